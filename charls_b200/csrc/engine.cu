@@ -1,0 +1,405 @@
+// engine.cu -- device resource management and kernel orchestration (see engine.hpp).
+#include "engine.hpp"
+
+#include "jls_interval.cuh"
+#include "jls_kernels.hpp"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+
+namespace jls {
+
+namespace {
+
+std::atomic<int> g_device{-1}; // -1: whatever device is current when the first engine is used
+
+constexpr size_t outcome_words = 4; // per job: status key, result[0], result[1], pad
+
+size_t align_up(size_t value, size_t alignment) noexcept
+{
+    return (value + alignment - 1) / alignment * alignment;
+}
+
+int32_t map_cuda_error(cudaError_t error, const char* what) noexcept
+{
+    if (error == cudaSuccess)
+        return 0;
+    std::fprintf(stderr, "charls_b200: CUDA failure in %s: %s\n", what, cudaGetErrorString(error));
+    cudaGetLastError(); // clear the sticky-free error state
+    return error == cudaErrorMemoryAllocation ? errc_not_enough_memory : errc_device_failure;
+}
+
+#define JLS_CUDA(expr)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const int32_t jls_cuda_status = map_cuda_error((expr), #expr);                                                 \
+        if (jls_cuda_status != 0)                                                                                      \
+            return jls_cuda_status;                                                                                    \
+    } while (0)
+
+#define JLS_CHECK(expr)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const int32_t jls_check_status = (expr);                                                                       \
+        if (jls_check_status != 0)                                                                                     \
+            return jls_check_status;                                                                                   \
+    } while (0)
+
+size_t row_bytes_of(const CodecParams& p) noexcept
+{
+    const size_t samples_per_pixel = p.interleave == ilv_none ? 1U : static_cast<size_t>(p.components);
+    return static_cast<size_t>(p.width) * samples_per_pixel * static_cast<size_t>(p.sample_bytes);
+}
+
+} // namespace
+
+int32_t set_device(int32_t ordinal) noexcept
+{
+    int count = 0;
+    JLS_CUDA(cudaGetDeviceCount(&count));
+    if (ordinal < 0 || ordinal >= count)
+        return 101; // invalid_argument
+    g_device.store(ordinal);
+    return 0;
+}
+
+int32_t device_count(int32_t* count) noexcept
+{
+    int n = 0;
+    JLS_CUDA(cudaGetDeviceCount(&n));
+    *count = n;
+    return 0;
+}
+
+Engine::~Engine()
+{
+    if (device_ >= 0)
+        cudaSetDevice(device_);
+    for (Buffer* b : {&pixels_, &stream_buffer_, &slots_, &interval_bytes_, &interval_offset_, &line_scratch_, &job_table_,
+                      &outcomes_, &marker_counts_, &marker_totals_, &marker_codes_, &header_, &pointer_table_, &prefixes_,
+                      &host_outcomes_, &host_jobs_, &host_prefixes_, &host_pointer_table_})
+        release(*b);
+    if (stream_)
+        cudaStreamDestroy(stream_);
+}
+
+void Engine::release(Buffer& buffer) noexcept
+{
+    if (buffer.data)
+    {
+        if (buffer.pinned)
+            cudaFreeHost(buffer.data);
+        else
+            cudaFree(buffer.data);
+    }
+    buffer = Buffer{};
+}
+
+int32_t Engine::prepare()
+{
+    int wanted = g_device.load();
+    if (wanted < 0)
+    {
+        JLS_CUDA(cudaGetDevice(&wanted));
+    }
+    if (device_ >= 0 && device_ != wanted)
+        return 100; // invalid_operation: an object stays on the device it was first used on
+    JLS_CUDA(cudaSetDevice(wanted));
+    device_ = wanted;
+    if (!stream_)
+        JLS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    return 0;
+}
+
+int32_t Engine::ensure(Buffer& buffer, size_t bytes, bool pinned)
+{
+    if (buffer.capacity >= bytes && buffer.data)
+        return 0;
+    release(buffer);
+    const size_t capacity = align_up(bytes + bytes / 8 + 256, 256);
+    void* data = nullptr;
+    if (pinned)
+        JLS_CUDA(cudaMallocHost(&data, capacity));
+    else
+        JLS_CUDA(cudaMalloc(&data, capacity));
+    buffer.data = data;
+    buffer.capacity = capacity;
+    buffer.pinned = pinned;
+    return 0;
+}
+
+int32_t Engine::stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream)
+{
+    const size_t n = jobs.size();
+    const size_t intervals = p.interval_count;
+    const bool general = !use_fast_path(p);
+    const size_t slots_per_job = encode ? intervals * slot_bytes : 0;
+    const size_t offsets_per_job = 2 * intervals + 2;
+    const size_t lines_per_job = general ? static_cast<size_t>(2) * p.components * (p.width + 2) * intervals : 0;
+
+    if (encode)
+    {
+        JLS_CHECK(ensure(slots_, n * slots_per_job + 64));
+        JLS_CHECK(ensure(interval_bytes_, n * intervals * sizeof(uint32_t)));
+    }
+    JLS_CHECK(ensure(interval_offset_, n * offsets_per_job * sizeof(uint64_t)));
+    if (general)
+        JLS_CHECK(ensure(line_scratch_, n * lines_per_job * sizeof(uint16_t) + 64));
+    JLS_CHECK(ensure(outcomes_, n * outcome_words * sizeof(uint64_t)));
+    JLS_CHECK(ensure(job_table_, n * sizeof(ScanJob)));
+    JLS_CHECK(ensure(host_jobs_, n * sizeof(ScanJob), true));
+
+    for (size_t i = 0; i < n; ++i)
+    {
+        ScanJob& job = jobs[i];
+        job.slots = encode ? static_cast<uint8_t*>(slots_.data) + i * slots_per_job : nullptr;
+        job.interval_bytes = encode ? static_cast<uint32_t*>(interval_bytes_.data) + i * intervals : nullptr;
+        job.interval_offset = static_cast<uint64_t*>(interval_offset_.data) + i * offsets_per_job;
+        job.line_scratch = general ? static_cast<uint16_t*>(line_scratch_.data) + i * lines_per_job : nullptr;
+        job.status = static_cast<uint64_t*>(outcomes_.data) + i * outcome_words;
+        job.result = job.status + 1;
+    }
+    std::memcpy(host_jobs_.data, jobs.data(), n * sizeof(ScanJob));
+    JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, n * sizeof(ScanJob), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+int32_t Engine::fetch_outcomes(size_t job_count, CUstream_st* stream)
+{
+    JLS_CHECK(ensure(host_outcomes_, job_count * outcome_words * sizeof(uint64_t), true));
+    JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, job_count * outcome_words * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, stream));
+    JLS_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI path: host buffers
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
+                                      size_t capacity, size_t& written)
+{
+    written = 0;
+    JLS_CHECK(prepare());
+    const uint64_t launches_before = kernel_launch_count();
+    const size_t row_bytes = row_bytes_of(p);
+    const size_t pitch = align_up(row_bytes, 16);
+    JLS_CHECK(ensure(pixels_, pitch * static_cast<size_t>(p.height) + 64));
+    if (stride == pitch)
+        JLS_CUDA(cudaMemcpyAsync(pixels_.data, source, pitch * (static_cast<size_t>(p.height) - 1) + row_bytes,
+                                 cudaMemcpyHostToDevice, stream_));
+    else
+        JLS_CUDA(cudaMemcpy2DAsync(pixels_.data, pitch, source, stride, row_bytes, static_cast<size_t>(p.height),
+                                   cudaMemcpyHostToDevice, stream_));
+
+    const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
+    const size_t worst_total = static_cast<size_t>(p.interval_count) * (slot_bytes + 2);
+    const size_t device_capacity = capacity < worst_total ? capacity : worst_total;
+    JLS_CHECK(ensure(stream_buffer_, device_capacity + 64));
+
+    std::vector<ScanJob> jobs(1);
+    jobs[0] = ScanJob{};
+    jobs[0].pixels_in = static_cast<const uint8_t*>(pixels_.data);
+    jobs[0].stride = pitch;
+    jobs[0].stream_out = static_cast<uint8_t*>(stream_buffer_.data);
+    jobs[0].stream_out_capacity = device_capacity;
+    JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_));
+    JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_));
+    JLS_CHECK(fetch_outcomes(1, stream_));
+    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+
+    const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
+    if (outcome[0] != ~0ULL)
+        return static_cast<int32_t>(outcome[0] & 0xFF);
+    const uint64_t total = outcome[1];
+    if (total > capacity)
+        return err_destination_too_small;
+    if (total != 0)
+    {
+        JLS_CUDA(cudaMemcpyAsync(destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
+        JLS_CUDA(cudaStreamSynchronize(stream_));
+    }
+    written = static_cast<size_t>(total);
+    return 0;
+}
+
+int32_t Engine::upload_stream(const uint8_t* host_stream, size_t size)
+{
+    JLS_CHECK(prepare());
+    JLS_CHECK(ensure(stream_buffer_, size + 64));
+    JLS_CUDA(cudaMemcpyAsync(stream_buffer_.data, host_stream, size, cudaMemcpyHostToDevice, stream_));
+    uploaded_stream_size_ = size;
+    return 0;
+}
+
+int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed)
+{
+    consumed = 0;
+    JLS_CHECK(prepare());
+    if (offset > uploaded_stream_size_)
+        return err_need_more_data;
+    const uint64_t launches_before = kernel_launch_count();
+    const size_t remaining = uploaded_stream_size_ - offset;
+    const size_t row_bytes = row_bytes_of(p);
+    const size_t pitch = align_up(row_bytes, 16);
+    JLS_CHECK(ensure(pixels_, pitch * static_cast<size_t>(p.height) + 64));
+
+    const size_t blocks = marker_blocks_for(remaining);
+    JLS_CHECK(ensure(marker_counts_, (blocks + 1) * sizeof(uint32_t)));
+    JLS_CHECK(ensure(marker_totals_, sizeof(uint32_t)));
+    JLS_CHECK(ensure(marker_codes_, p.interval_count));
+
+    std::vector<ScanJob> jobs(1);
+    jobs[0] = ScanJob{};
+    jobs[0].pixels_out = static_cast<uint8_t*>(pixels_.data);
+    jobs[0].stride = pitch;
+    jobs[0].stream_in = static_cast<const uint8_t*>(stream_buffer_.data) + offset;
+    jobs[0].stream_in_size = remaining;
+    JLS_CHECK(stage_jobs(p, jobs, false, 0, stream_));
+    JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), 1, remaining,
+                           static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
+                           static_cast<uint8_t*>(marker_codes_.data), stream_));
+    JLS_CHECK(fetch_outcomes(1, stream_));
+    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+
+    const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
+    if (outcome[0] != ~0ULL)
+        return static_cast<int32_t>(outcome[0] & 0xFF);
+    consumed = static_cast<size_t>(outcome[1]);
+    JLS_CUDA(cudaMemcpy2DAsync(destination, stride, pixels_.data, pitch, row_bytes, static_cast<size_t>(p.height),
+                               cudaMemcpyDeviceToHost, stream_));
+    JLS_CUDA(cudaStreamSynchronize(stream_));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batch path: device-resident frames
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
+                             size_t stride, CUstream_st* user_stream)
+{
+    JLS_CHECK(prepare());
+    if (count == 0)
+        return 0;
+    cudaStream_t stream = user_stream ? user_stream : stream_;
+    const uint64_t launches_before = kernel_launch_count();
+    const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
+
+    JLS_CHECK(ensure(header_, header_size + 16));
+    JLS_CHECK(ensure(host_prefixes_, header_size + 16, true));
+    std::memcpy(host_prefixes_.data, header, header_size);
+    JLS_CUDA(cudaMemcpyAsync(header_.data, host_prefixes_.data, header_size, cudaMemcpyHostToDevice, stream));
+
+    std::vector<ScanJob> jobs(count);
+    for (size_t i = 0; i < count; ++i)
+    {
+        ScanJob& job = jobs[i];
+        job = ScanJob{};
+        job.pixels_in = frames[i].pixels;
+        job.stride = stride;
+        const bool room = frames[i].stream_capacity >= header_size + 2;
+        job.stream_out = frames[i].stream + header_size;
+        job.stream_out_capacity = room ? frames[i].stream_capacity - header_size - 2 : 0;
+    }
+    JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream));
+    const ScanJob* device_jobs = static_cast<const ScanJob*>(job_table_.data);
+    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream));
+    JLS_CUDA(launch_wrap_frames(device_jobs, static_cast<const uint8_t*>(header_.data), static_cast<uint32_t>(header_size),
+                                static_cast<uint32_t>(count), stream));
+    JLS_CHECK(fetch_outcomes(count, stream));
+    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+
+    int32_t first_error = 0;
+    const uint64_t* outcomes = static_cast<const uint64_t*>(host_outcomes_.data);
+    for (size_t i = 0; i < count; ++i)
+    {
+        const uint64_t* outcome = outcomes + i * outcome_words;
+        int32_t status = outcome[0] != ~0ULL ? static_cast<int32_t>(outcome[0] & 0xFF) : 0;
+        if (status == 0 && outcome[1] > jobs[i].stream_out_capacity)
+            status = err_destination_too_small;
+        frames[i].status = status;
+        frames[i].stream_size = status == 0 ? header_size + static_cast<size_t>(outcome[1]) + 2 : 0;
+        if (status != 0 && first_error == 0)
+            first_error = status;
+    }
+    return first_error;
+}
+
+int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, std::vector<uint8_t>& prefixes,
+                                  CUstream_st* user_stream)
+{
+    JLS_CHECK(prepare());
+    cudaStream_t stream = user_stream ? user_stream : stream_;
+    const size_t table_bytes = count * (sizeof(void*) + sizeof(size_t));
+    JLS_CHECK(ensure(pointer_table_, table_bytes));
+    JLS_CHECK(ensure(host_pointer_table_, table_bytes, true));
+    JLS_CHECK(ensure(prefixes_, count * prefix_bytes));
+    JLS_CHECK(ensure(host_prefixes_, count * prefix_bytes, true));
+    auto** host_pointers = static_cast<const uint8_t**>(host_pointer_table_.data);
+    auto* host_sizes = reinterpret_cast<size_t*>(host_pointers + count);
+    for (size_t i = 0; i < count; ++i)
+    {
+        host_pointers[i] = frames[i].stream;
+        host_sizes[i] = frames[i].stream_capacity;
+    }
+    JLS_CUDA(cudaMemcpyAsync(pointer_table_.data, host_pointer_table_.data, table_bytes, cudaMemcpyHostToDevice, stream));
+    auto** device_pointers = static_cast<const uint8_t**>(pointer_table_.data);
+    JLS_CUDA(launch_copy_prefixes(device_pointers, reinterpret_cast<const size_t*>(device_pointers + count),
+                                  static_cast<uint8_t*>(prefixes_.data), prefix_bytes, static_cast<uint32_t>(count), stream));
+    JLS_CUDA(cudaMemcpyAsync(host_prefixes_.data, prefixes_.data, count * prefix_bytes, cudaMemcpyDeviceToHost, stream));
+    JLS_CUDA(cudaStreamSynchronize(stream));
+    prefixes.assign(static_cast<const uint8_t*>(host_prefixes_.data),
+                    static_cast<const uint8_t*>(host_prefixes_.data) + count * prefix_bytes);
+    return 0;
+}
+
+int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream)
+{
+    JLS_CHECK(prepare());
+    if (count == 0)
+        return 0;
+    cudaStream_t stream = user_stream ? user_stream : stream_;
+    const uint64_t launches_before = kernel_launch_count();
+
+    size_t max_remaining = 0;
+    std::vector<ScanJob> jobs(count);
+    for (size_t i = 0; i < count; ++i)
+    {
+        ScanJob& job = jobs[i];
+        job = ScanJob{};
+        job.pixels_out = frames[i].pixels;
+        job.stride = stride;
+        job.stream_in = frames[i].stream + frames[i].scan_offset;
+        job.stream_in_size = frames[i].stream_capacity - frames[i].scan_offset;
+        max_remaining = job.stream_in_size > max_remaining ? job.stream_in_size : max_remaining;
+    }
+    const size_t blocks = marker_blocks_for(max_remaining);
+    JLS_CHECK(ensure(marker_counts_, count * (blocks + 1) * sizeof(uint32_t)));
+    JLS_CHECK(ensure(marker_totals_, count * sizeof(uint32_t)));
+    JLS_CHECK(ensure(marker_codes_, count * p.interval_count));
+    JLS_CHECK(stage_jobs(p, jobs, false, 0, stream));
+    JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), static_cast<uint32_t>(count), max_remaining,
+                           static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
+                           static_cast<uint8_t*>(marker_codes_.data), stream));
+    JLS_CHECK(fetch_outcomes(count, stream));
+    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+
+    int32_t first_error = 0;
+    const uint64_t* outcomes = static_cast<const uint64_t*>(host_outcomes_.data);
+    for (size_t i = 0; i < count; ++i)
+    {
+        const uint64_t* outcome = outcomes + i * outcome_words;
+        int32_t status = outcome[0] != ~0ULL ? static_cast<int32_t>(outcome[0] & 0xFF) : 0;
+        if (status == 0 && outcome[2] != 0xD9)
+            status = 24; // end_of_image_marker_not_found (reference src/jpeg_stream_reader.cpp:152-172)
+        frames[i].status = status;
+        frames[i].stream_size = frames[i].scan_offset + static_cast<size_t>(outcome[1]) + 2;
+        if (status != 0 && first_error == 0)
+            first_error = status;
+    }
+    return first_error;
+}
+
+} // namespace jls

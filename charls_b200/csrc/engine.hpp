@@ -1,0 +1,92 @@
+// engine.hpp -- host-side owner of the device resources behind one encoder / decoder / batch object.
+//
+// The engine is the seam the reference has between its C ABI objects and make_scan_codec()
+// (reference src/charls_jpegls_encoder.cpp:285-296, src/charls_jpegls_decoder.cpp:186-189): the ABI layer hands it one
+// scan at a time (host buffers), or a whole batch of device-resident frames, and it runs the kernels.
+// One engine = one CUDA stream + grow-only device buffers; engines of different objects are independent, so distinct
+// encoder / decoder instances may be used from different host threads concurrently (like the reference's instances).
+#pragma once
+
+#include "jls_common.h"
+#include "jls_params.hpp"
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+struct CUstream_st;
+
+namespace jls {
+
+// error code for CUDA failures (no counterpart in the reference's charls_jpegls_errc)
+constexpr int32_t errc_device_failure = 200;
+constexpr int32_t errc_not_enough_memory = 1;
+
+int32_t set_device(int32_t ordinal) noexcept; // process-wide device used by every engine
+int32_t device_count(int32_t* count) noexcept;
+
+struct BatchFrame
+{
+    uint8_t* pixels;        // device
+    uint8_t* stream;        // device
+    size_t stream_capacity; // encode: capacity; decode: stream size
+    size_t stream_size;     // encode out
+    int32_t status;         // out
+    // decode only, filled by the caller after parsing the header on the host:
+    size_t scan_offset; // offset of the first entropy-coded byte
+};
+
+class Engine final
+{
+public:
+    Engine() = default;
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    // Encodes one scan whose samples are in host memory at `source` (line pitch `stride`) and writes the entropy-coded
+    // data (interval data + RSTm markers) to host memory at `destination`.  Returns a charls_jpegls_errc.
+    int32_t encode_scan_from_host(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
+                                  size_t capacity, size_t& written);
+
+    // Copies a complete JPEG-LS stream to the device once; decode_scan_to_host then works on offsets into it.
+    int32_t upload_stream(const uint8_t* host_stream, size_t size);
+    // Decodes the scan whose entropy-coded data starts `offset` bytes into the uploaded stream.
+    // `consumed` = bytes of entropy-coded data (up to the marker that ends the scan).
+    int32_t decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed);
+
+    // Device-resident batches (single-scan frames).  `header` = the bytes in front of the entropy-coded data.
+    int32_t encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
+                         size_t stride, CUstream_st* user_stream);
+    int32_t decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream);
+    // Downloads the first `prefix_bytes` of every frame's stream (header parsing happens on the host).
+    int32_t download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, std::vector<uint8_t>& prefixes,
+                              CUstream_st* user_stream);
+
+    uint32_t last_kernel_launches() const noexcept { return last_launches_; }
+
+private:
+    struct Buffer
+    {
+        void* data{};
+        size_t capacity{};
+        bool pinned{};
+    };
+
+    int32_t prepare();
+    int32_t ensure(Buffer& buffer, size_t bytes, bool pinned = false);
+    void release(Buffer& buffer) noexcept;
+    // Lays out the per-job scratch for `job_count` jobs and uploads the job table. Scratch pointers are filled in here.
+    int32_t stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream);
+    int32_t fetch_outcomes(size_t job_count, CUstream_st* stream);
+
+    CUstream_st* stream_{};
+    int device_{-1};
+    Buffer pixels_, stream_buffer_, slots_, interval_bytes_, interval_offset_, line_scratch_, job_table_, outcomes_,
+        marker_counts_, marker_totals_, marker_codes_, header_, pointer_table_, prefixes_;
+    Buffer host_outcomes_, host_jobs_, host_prefixes_, host_pointer_table_; // pinned
+    size_t uploaded_stream_size_{};
+    uint32_t last_launches_{};
+};
+
+} // namespace jls

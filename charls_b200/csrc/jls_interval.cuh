@@ -1,0 +1,304 @@
+// jls_interval.cuh -- what ONE thread does for ONE restart interval (encode or decode), fast and general path.
+//
+// Kept apart from the __global__ wrappers so that the unit tests can run exactly this code on the CPU
+// (tests/hostemu) -- the kernels in jls_kernels.cu add nothing but the thread -> interval mapping, the shared-memory
+// context storage and the atomic error reporting.
+#pragma once
+
+#include "jls_codec.cuh"
+
+namespace jls {
+
+// Outcome of coding one interval: 0 or the charls_jpegls_errc to report for it.
+struct IntervalResult
+{
+    int32_t errc;
+    uint32_t bytes; // encode: size of the interval's entropy data
+};
+
+// One component of pixel x of a line-interleaved source line (masking / colour transform like load_pixel).
+JLS_HD int32_t load_line_component(const CodecParams& p, const uint8_t* line, int32_t x, int32_t c)
+{
+    if (p.components == 3)
+    {
+        int32_t v[3];
+        load_pixel<3>(p, line, x, v);
+        return v[c];
+    }
+    const int32_t mask = (1 << p.bits_per_sample) - 1;
+    return load_sample(line, x * p.components + c, p.sample_bytes) & mask;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path, restart interval = 1 line
+// ---------------------------------------------------------------------------------------------------------------------
+template<int NC, bool LOSSLESS>
+JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
+                                           RegularContext* contexts, int32_t context_stride, size_t slot_bytes)
+{
+    FastLineEncoder<NC, LOSSLESS> enc;
+    enc.begin(p, contexts, context_stride, job.slots + static_cast<size_t>(interval) * slot_bytes, slot_bytes);
+    const uint8_t* line = job.pixels_in + static_cast<size_t>(interval) * job.stride;
+    const int32_t width = p.width;
+
+    bool coded = false;
+    if constexpr (NC == 1)
+    {
+        if (p.interleave == ilv_line)
+        {
+            // one line of every component forms the interval; contexts are shared, the run index restarts per component
+            // (reference src/scan_decoder_impl.hpp:76-117,122-127)
+            for (int32_t c = 0; c < p.components; ++c)
+            {
+                enc.begin_line();
+                enc.run_count = 0;
+                for (int32_t x = 0; x < width; ++x)
+                {
+                    const int32_t v[1] = {load_line_component(p, line, x, c)};
+                    enc.pixel(p, v, x == width - 1);
+                }
+            }
+            coded = true;
+        }
+    }
+    if (!coded)
+    {
+        for (int32_t x = 0; x < width; ++x)
+        {
+            int32_t v[NC];
+            load_pixel<NC>(p, line, x, v);
+            enc.pixel(p, v, x == width - 1);
+        }
+    }
+
+    IntervalResult result;
+    result.bytes = enc.finish();
+    result.errc = enc.bw.overflow ? err_destination_too_small : (enc.bad ? err_invalid_data : err_none);
+    return result;
+}
+
+// What the reference checks when an interval / the scan ends (src/scan_decoder.hpp:71-89,335-349).
+JLS_HD int32_t interval_end_status(const CodecParams& p, const BitReader& br, bool bad, uint32_t interval)
+{
+    if (bad || br.overrun())
+        return err_invalid_data;
+    if (interval + 1 == p.interval_count)
+    {
+        // left-over bits must be zero padding and the closing marker must follow directly
+        return (br.cache != 0 || br.unread_bytes() > 0) ? err_invalid_data : err_none;
+    }
+    // the reference looks for RSTm where its 64-bit read cache stopped
+    return br.unread_bytes() > 7 ? err_restart_marker_not_found : err_none;
+}
+
+template<int NC, bool LOSSLESS>
+JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
+                                           RegularContext* contexts, int32_t context_stride)
+{
+    IntervalResult result = {err_none, 0};
+    // interval_offset holds 2 entries per interval: [2i] = first byte, [2i+1] = end (first 0xFF of the closing marker)
+    const uint64_t begin = job.interval_offset[2 * static_cast<size_t>(interval)];
+    const uint64_t end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
+    if (end == ~0ULL || begin == ~0ULL || begin > end)
+        return result; // marker table incomplete: the finish step reports it
+
+    FastLineDecoder<NC, LOSSLESS> dec;
+    dec.begin(p, contexts, context_stride, job.stream_in + begin, job.stream_in + end);
+    uint8_t* line = job.pixels_out + static_cast<size_t>(interval) * job.stride;
+    const int32_t width = p.width;
+
+    bool coded = false;
+    if constexpr (NC == 1)
+    {
+        if (p.interleave == ilv_line)
+        {
+            const int32_t nc = p.components;
+            for (int32_t c = 0; c < nc; ++c)
+            {
+                dec.begin_line();
+                for (int32_t x = 0; x < width; ++x)
+                {
+                    dec.pixel(p, width - x);
+                    store_sample(line, x * nc + c, p.sample_bytes, dec.ra[0]);
+                }
+            }
+            if (nc == 3 && p.transform != 0)
+            {
+                // inverse colour transform in place once all three component lines are there
+                for (int32_t x = 0; x < width; ++x)
+                {
+                    int32_t v[3];
+                    for (int32_t c = 0; c < 3; ++c)
+                        v[c] = load_sample(line, x * 3 + c, p.sample_bytes);
+                    store_pixel<3>(p, line, x, v);
+                }
+            }
+            coded = true;
+        }
+    }
+    if (!coded)
+    {
+        for (int32_t x = 0; x < width; ++x)
+        {
+            dec.pixel(p, width - x);
+            store_pixel<NC>(p, line, x, dec.ra);
+        }
+    }
+    result.errc = interval_end_status(p, dec.br, dec.bad, interval);
+    return result;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// General path: any restart interval, full 2-D LOCO-I
+// ---------------------------------------------------------------------------------------------------------------------
+JLS_HD void general_set_edges(uint16_t* cur, uint16_t* prev, int32_t nc, int32_t width)
+{
+    const int32_t ps = width + 2;
+    for (int32_t c = 0; c < nc; ++c)
+    {
+        prev[c * ps + width + 1] = prev[c * ps + width]; // reference src/scan_codec.hpp:189-195
+        cur[c * ps] = prev[c * ps + 1];
+    }
+}
+
+template<bool LOSSLESS>
+JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval,
+                                                       size_t slot_bytes)
+{
+    const int32_t width = p.width, ps = width + 2, nc = p.components;
+    const size_t per_interval = static_cast<size_t>(2) * nc * ps;
+    uint16_t* lines = job.line_scratch + static_cast<size_t>(interval) * per_interval;
+    for (size_t i = 0; i < per_interval; ++i)
+        lines[i] = 0;
+
+    GeneralState state;
+    state.reset(p);
+    state.bad = false;
+    int32_t run_index[4] = {0, 0, 0, 0};
+    BitWriter bw;
+    bw.init(job.slots + static_cast<size_t>(interval) * slot_bytes, slot_bytes);
+
+    const uint32_t first_line = interval * p.lines_per_interval;
+    const uint32_t line_end = static_cast<uint32_t>(
+        imin(static_cast<int32_t>(first_line + p.lines_per_interval), p.height)); // heights are <= 100000
+    for (uint32_t line = first_line; line < line_end; ++line)
+    {
+        uint16_t* cur = lines + ((line - first_line) & 1U) * (static_cast<size_t>(nc) * ps);
+        uint16_t* prev = lines + (((line - first_line) & 1U) ^ 1U) * (static_cast<size_t>(nc) * ps);
+        const uint8_t* source = job.pixels_in + static_cast<size_t>(line) * job.stride;
+
+        // caller layout -> component lines (reference src/copy_to_line_buffer.hpp:26-261)
+        for (int32_t x = 0; x < width; ++x)
+        {
+            if (nc == 1)
+            {
+                int32_t v[1];
+                load_pixel<1>(p, source, x, v);
+                cur[x + 1] = static_cast<uint16_t>(v[0]);
+            }
+            else
+            {
+                for (int32_t c = 0; c < nc; ++c)
+                    cur[c * ps + x + 1] = static_cast<uint16_t>(load_line_component(p, source, x, c));
+            }
+        }
+        general_set_edges(cur, prev, nc, width);
+        if (p.interleave == ilv_sample)
+        {
+            state.run_index = run_index[0];
+            general_encode_line_multi<LOSSLESS>(p, state, bw, cur, prev);
+            run_index[0] = state.run_index;
+        }
+        else
+        {
+            for (int32_t c = 0; c < nc; ++c)
+            {
+                state.run_index = run_index[c];
+                general_encode_line<LOSSLESS>(p, state, bw, cur + c * ps, prev + c * ps);
+                run_index[c] = state.run_index;
+            }
+        }
+    }
+
+    IntervalResult result;
+    result.bytes = bw.finish();
+    result.errc = bw.overflow ? err_destination_too_small : (state.bad ? err_invalid_data : err_none);
+    return result;
+}
+
+template<bool LOSSLESS>
+JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval)
+{
+    IntervalResult result = {err_none, 0};
+    const uint64_t begin = job.interval_offset[2 * static_cast<size_t>(interval)];
+    const uint64_t end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
+    if (end == ~0ULL || begin == ~0ULL || begin > end)
+        return result;
+
+    const int32_t width = p.width, ps = width + 2, nc = p.components;
+    const size_t per_interval = static_cast<size_t>(2) * nc * ps;
+    uint16_t* lines = job.line_scratch + static_cast<size_t>(interval) * per_interval;
+    for (size_t i = 0; i < per_interval; ++i)
+        lines[i] = 0;
+
+    GeneralState state;
+    state.reset(p);
+    state.bad = false;
+    int32_t run_index[4] = {0, 0, 0, 0};
+    BitReader br;
+    br.init(job.stream_in + begin, job.stream_in + end);
+
+    const uint32_t first_line = interval * p.lines_per_interval;
+    const uint32_t line_end = static_cast<uint32_t>(imin(static_cast<int32_t>(first_line + p.lines_per_interval), p.height));
+    for (uint32_t line = first_line; line < line_end && !state.bad; ++line)
+    {
+        uint16_t* cur = lines + ((line - first_line) & 1U) * (static_cast<size_t>(nc) * ps);
+        uint16_t* prev = lines + (((line - first_line) & 1U) ^ 1U) * (static_cast<size_t>(nc) * ps);
+        general_set_edges(cur, prev, nc, width);
+        if (p.interleave == ilv_sample)
+        {
+            state.run_index = run_index[0];
+            general_decode_line_multi<LOSSLESS>(p, state, br, cur, prev);
+            run_index[0] = state.run_index;
+        }
+        else
+        {
+            for (int32_t c = 0; c < nc && !state.bad; ++c)
+            {
+                state.run_index = run_index[c];
+                general_decode_line<LOSSLESS>(p, state, br, cur + c * ps, prev + c * ps);
+                run_index[c] = state.run_index;
+            }
+        }
+        if (state.bad)
+            break;
+
+        // component lines -> caller layout (reference src/copy_from_line_buffer.hpp:24-191)
+        uint8_t* destination = job.pixels_out + static_cast<size_t>(line) * job.stride;
+        for (int32_t x = 0; x < width; ++x)
+        {
+            if (nc == 3)
+            {
+                const int32_t v[3] = {cur[x + 1], cur[ps + x + 1], cur[2 * ps + x + 1]};
+                store_pixel<3>(p, destination, x, v);
+            }
+            else
+            {
+                for (int32_t c = 0; c < nc; ++c)
+                    store_sample(destination, x * nc + c, p.sample_bytes, cur[c * ps + x + 1]);
+            }
+        }
+    }
+    result.errc = interval_end_status(p, br, state.bad, interval);
+    return result;
+}
+
+// Which intervals take the fast path: one line per interval; scalar lines (ILV none / line) or 3-component pixels.
+inline bool use_fast_path(const CodecParams& p)
+{
+    if (p.lines_per_interval != 1)
+        return false;
+    return p.interleave != ilv_sample || p.components == 3;
+}
+
+} // namespace jls

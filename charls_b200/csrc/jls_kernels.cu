@@ -1,0 +1,547 @@
+// jls_kernels.cu -- sm_100a kernels of the JPEG-LS scan engine and their launch wrappers.
+//
+// Pipeline (DESIGN.md "Kernels"):
+//   encode:  k_encode_fast / k_encode_general  -> one slot of entropy bytes per restart interval
+//            k_scan_offsets                    -> exclusive scan of the interval sizes (+2 per RSTm marker)
+//            k_gather                          -> concatenation of the intervals, RSTm markers inserted
+//   decode:  k_marker_count / k_marker_scan / k_marker_write -> ordered table of the markers that delimit intervals
+//            k_decode_fast / k_decode_general  -> samples
+//            k_decode_finish                   -> marker-sequence validation, bytes consumed by the scan
+// A thread owns one restart interval from its first to its last bit: the adaptive coder is a strict serial chain in x
+// (every symbol's context state and, in the decoder, bit position depend on the previous symbol), so the parallel
+// axes are intervals x images.  There is no dense contraction anywhere: the tensor cores are not used.
+#include "jls_kernels.hpp"
+
+#include "jls_interval.cuh"
+
+#include <cuda_runtime.h>
+
+namespace jls {
+
+namespace {
+
+constexpr int fast_block_threads = 128;
+constexpr int general_block_threads = 32;
+
+std::atomic<uint64_t> g_kernel_launches{0};
+
+// first error in stream order wins: key = (interval << 8) | errc, smaller interval first
+__device__ __forceinline__ void report_error(const ScanJob& job, uint32_t interval, int32_t errc)
+{
+    const unsigned long long key = (static_cast<unsigned long long>(interval) << 8) | static_cast<unsigned long long>(errc);
+    atomicMin(reinterpret_cast<unsigned long long*>(job.status), key);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path, restart interval = 1 line: one thread per line, a warp holds 32 consecutive lines.  The five regular
+// contexts of a thread live in shared memory as [context][thread] so that a warp-wide 16-byte access is conflict free.
+// ---------------------------------------------------------------------------------------------------------------------
+template<int NC, bool LOSSLESS>
+__global__ void __launch_bounds__(fast_block_threads)
+    k_encode_fast(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
+{
+    __shared__ RegularContext contexts[5 * fast_block_threads];
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t interval = blockIdx.x * fast_block_threads + threadIdx.x;
+    if (interval >= p.interval_count)
+        return;
+    const IntervalResult r =
+        encode_interval_fast<NC, LOSSLESS>(p, job, interval, contexts + threadIdx.x, fast_block_threads, slot_bytes);
+    job.interval_bytes[interval] = r.bytes;
+    if (r.errc != err_none)
+        report_error(job, interval, r.errc);
+}
+
+template<int NC, bool LOSSLESS>
+__global__ void __launch_bounds__(fast_block_threads)
+    k_decode_fast(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
+{
+    __shared__ RegularContext contexts[5 * fast_block_threads];
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t interval = blockIdx.x * fast_block_threads + threadIdx.x;
+    if (interval >= p.interval_count)
+        return;
+    const IntervalResult r = decode_interval_fast<NC, LOSSLESS>(p, job, interval, contexts + threadIdx.x, fast_block_threads);
+    if (r.errc != err_none)
+        report_error(job, interval, r.errc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// General path: one thread per restart interval, full 2-D LOCO-I (365 contexts in local memory).
+// ---------------------------------------------------------------------------------------------------------------------
+template<bool LOSSLESS>
+__global__ void __launch_bounds__(general_block_threads)
+    k_encode_general(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t interval = blockIdx.x * general_block_threads + threadIdx.x;
+    if (interval >= p.interval_count)
+        return;
+    const IntervalResult r = encode_interval_general<LOSSLESS>(p, job, interval, slot_bytes);
+    job.interval_bytes[interval] = r.bytes;
+    if (r.errc != err_none)
+        report_error(job, interval, r.errc);
+}
+
+template<bool LOSSLESS>
+__global__ void __launch_bounds__(general_block_threads)
+    k_decode_general(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t interval = blockIdx.x * general_block_threads + threadIdx.x;
+    if (interval >= p.interval_count)
+        return;
+    const IntervalResult r = decode_interval_general<LOSSLESS>(p, job, interval);
+    if (r.errc != err_none)
+        report_error(job, interval, r.errc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Encode: interval sizes -> offsets -> contiguous stream with RSTm markers
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int scan_block_threads = 1024;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t value, uint64_t* warp_totals, uint64_t& block_total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t inclusive = value;
+#pragma unroll
+    for (int delta = 1; delta < 32; delta <<= 1)
+    {
+        const uint64_t other = __shfl_up_sync(0xFFFFFFFFU, inclusive, delta);
+        if (lane >= delta)
+            inclusive += other;
+    }
+    if (lane == 31)
+        warp_totals[warp] = inclusive;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint64_t t = lane < (blockDim.x >> 5) ? warp_totals[lane] : 0;
+        uint64_t inc = t;
+#pragma unroll
+        for (int delta = 1; delta < 32; delta <<= 1)
+        {
+            const uint64_t other = __shfl_up_sync(0xFFFFFFFFU, inc, delta);
+            if (lane >= delta)
+                inc += other;
+        }
+        warp_totals[lane] = inc - t; // exclusive prefix of the warp totals
+        if (lane == 31)
+            warp_totals[32] = inc;
+    }
+    __syncthreads();
+    block_total = warp_totals[32];
+    const uint64_t result = warp_totals[warp] + inclusive - value;
+    __syncthreads();
+    return result;
+}
+
+// one block per job
+__global__ void __launch_bounds__(scan_block_threads)
+    k_scan_offsets(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
+{
+    __shared__ uint64_t warp_totals[33];
+    const ScanJob& job = jobs[blockIdx.x];
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < p.interval_count; base += scan_block_threads)
+    {
+        const uint32_t i = base + threadIdx.x;
+        uint64_t size = 0;
+        if (i < p.interval_count)
+            size = static_cast<uint64_t>(job.interval_bytes[i]) + (i + 1 < p.interval_count ? 2U : 0U);
+        uint64_t total;
+        const uint64_t offset = carry + block_exclusive_scan(size, warp_totals, total);
+        if (i < p.interval_count)
+            job.interval_offset[i] = offset;
+        carry += total;
+    }
+    if (threadIdx.x == 0)
+    {
+        job.interval_offset[p.interval_count] = carry;
+        job.result[0] = carry;
+        if (carry > job.stream_out_capacity)
+            atomicMin(reinterpret_cast<unsigned long long*>(job.status),
+                      (static_cast<unsigned long long>(p.interval_count) << 8) | err_destination_too_small);
+    }
+}
+
+// one warp per interval: slot -> final position, then the RSTm marker (reference decoder expects FF D0+(n mod 8))
+constexpr int gather_block_threads = 256;
+
+__global__ void __launch_bounds__(gather_block_threads)
+    k_gather(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t interval = blockIdx.x * (gather_block_threads / 32) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (interval >= p.interval_count)
+        return;
+    const uint64_t total = job.interval_offset[p.interval_count];
+    if (total > job.stream_out_capacity)
+        return;
+    const uint32_t bytes = job.interval_bytes[interval];
+    const uint8_t* source = job.slots + static_cast<size_t>(interval) * slot_bytes;
+    uint8_t* destination = job.stream_out + job.interval_offset[interval];
+
+    // head: bytes until the destination is 4-byte aligned; body: aligned 32-bit stores fed by two aligned loads and a
+    // funnel shift; tail: bytes
+    const uint32_t head = min(bytes, static_cast<uint32_t>((4U - (reinterpret_cast<uintptr_t>(destination) & 3U)) & 3U));
+    if (lane < head)
+        destination[lane] = source[lane];
+    const uint32_t body_words = (bytes - head) / 4U;
+    const uint32_t* source_words = reinterpret_cast<const uint32_t*>(source + (head & ~3U)); // slots are 16-byte aligned
+    const uint32_t shift = (head & 3U) * 8U;
+    uint32_t* destination_words = reinterpret_cast<uint32_t*>(destination + head);
+    for (uint32_t w = lane; w < body_words; w += 32)
+    {
+        const uint32_t lo = source_words[w];
+        const uint32_t hi = shift ? source_words[w + 1] : 0U;
+        destination_words[w] = __funnelshift_r(lo, hi, shift);
+    }
+    const uint32_t done = head + body_words * 4U;
+    if (lane < bytes - done)
+        destination[done + lane] = source[done + lane];
+    if (lane == 0 && interval + 1 < p.interval_count)
+    {
+        destination[bytes] = 0xFF;
+        destination[bytes + 1] = static_cast<uint8_t>(0xD0 + (interval & 7U));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode front end: ordered table of markers.  A marker is a byte >= 0x80 (and != 0xFF) that follows a 0xFF; inside
+// entropy-coded data 0xFF is always followed by a byte < 0x80 (T.87 A.1), so this is unambiguous.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int marker_block_threads = 256;
+constexpr int marker_bytes_per_thread = 16;
+constexpr int marker_bytes_per_block = marker_block_threads * marker_bytes_per_thread;
+
+__device__ __forceinline__ uint32_t marker_mask_of_thread(const uint8_t* data, size_t size, size_t first)
+{
+    // bit i set <=> data[first + i] is a marker code byte
+    uint32_t mask = 0;
+    if (first >= size)
+        return 0;
+    uint32_t previous = first > 0 ? data[first - 1] : 0U;
+    const size_t count = min(static_cast<size_t>(marker_bytes_per_thread), size - first);
+    for (size_t i = 0; i < count; ++i)
+    {
+        const uint32_t b = data[first + i];
+        if (previous == 0xFFU && b >= 0x80U && b != 0xFFU)
+            mask |= 1U << i;
+        previous = b;
+    }
+    return mask;
+}
+
+// grid (blocks, jobs): block_counts[job][block]
+__global__ void __launch_bounds__(marker_block_threads)
+    k_marker_count(const ScanJob* __restrict__ jobs, uint32_t* __restrict__ block_counts, uint32_t blocks_per_job)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const size_t first = static_cast<size_t>(blockIdx.x) * marker_bytes_per_block +
+                         static_cast<size_t>(threadIdx.x) * marker_bytes_per_thread;
+    const uint32_t count = __popc(marker_mask_of_thread(job.stream_in, job.stream_in_size, first));
+    __shared__ uint32_t warp_sums[marker_block_threads / 32];
+    uint32_t sum = count;
+#pragma unroll
+    for (int delta = 16; delta > 0; delta >>= 1)
+        sum += __shfl_down_sync(0xFFFFFFFFU, sum, delta);
+    if ((threadIdx.x & 31) == 0)
+        warp_sums[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t block_sum = 0;
+        for (int w = 0; w < marker_block_threads / 32; ++w)
+            block_sum += warp_sums[w];
+        block_counts[static_cast<size_t>(blockIdx.y) * blocks_per_job + blockIdx.x] = block_sum;
+    }
+}
+
+// one block per job: exclusive scan of the per-block counts (in place)
+__global__ void __launch_bounds__(scan_block_threads)
+    k_marker_scan(uint32_t* __restrict__ block_counts, uint32_t blocks_per_job, uint32_t* __restrict__ marker_totals)
+{
+    __shared__ uint64_t warp_totals[33];
+    uint32_t* counts = block_counts + static_cast<size_t>(blockIdx.x) * blocks_per_job;
+    uint64_t carry = 0;
+    for (uint32_t base = 0; base < blocks_per_job; base += scan_block_threads)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t value = i < blocks_per_job ? counts[i] : 0;
+        uint64_t total;
+        const uint64_t offset = carry + block_exclusive_scan(value, warp_totals, total);
+        if (i < blocks_per_job)
+            counts[i] = static_cast<uint32_t>(offset);
+        carry += total;
+    }
+    if (threadIdx.x == 0)
+        marker_totals[blockIdx.x] = static_cast<uint32_t>(carry);
+}
+
+// Writes interval_offset[2i] / [2i+1] (begin / end of interval i) for the first interval_count markers and remembers
+// each marker's code in marker_codes[job][i].
+__global__ void __launch_bounds__(marker_block_threads)
+    k_marker_write(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
+                   const uint32_t* __restrict__ block_counts, uint32_t blocks_per_job, uint8_t* __restrict__ marker_codes)
+{
+    __shared__ uint32_t warp_sums[marker_block_threads / 32];
+    const ScanJob& job = jobs[blockIdx.y];
+    const size_t first = static_cast<size_t>(blockIdx.x) * marker_bytes_per_block +
+                         static_cast<size_t>(threadIdx.x) * marker_bytes_per_thread;
+    const uint32_t mask = marker_mask_of_thread(job.stream_in, job.stream_in_size, first);
+    const uint32_t count = __popc(mask);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inclusive = count;
+#pragma unroll
+    for (int delta = 1; delta < 32; delta <<= 1)
+    {
+        const uint32_t other = __shfl_up_sync(0xFFFFFFFFU, inclusive, delta);
+        if (lane >= delta)
+            inclusive += other;
+    }
+    if (lane == 31)
+        warp_sums[warp] = inclusive;
+    __syncthreads();
+    uint32_t rank = block_counts[static_cast<size_t>(blockIdx.y) * blocks_per_job + blockIdx.x] + inclusive - count;
+    for (int w = 0; w < warp; ++w)
+        rank += warp_sums[w];
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        job.interval_offset[0] = 0;
+
+    uint32_t remaining = mask;
+    while (remaining != 0 && rank < p.interval_count)
+    {
+        const uint32_t bit = __ffs(remaining) - 1;
+        remaining &= remaining - 1;
+        const size_t code_position = first + bit;
+        size_t marker_begin = code_position - 1;
+        while (marker_begin > 0 && job.stream_in[marker_begin - 1] == 0xFF) // fill bytes (T.81 B.1.1.2)
+            --marker_begin;
+        job.interval_offset[2 * static_cast<size_t>(rank) + 1] = marker_begin;
+        if (rank + 1 < p.interval_count)
+            job.interval_offset[2 * static_cast<size_t>(rank) + 2] = code_position + 1;
+        marker_codes[static_cast<size_t>(blockIdx.y) * p.interval_count + rank] = job.stream_in[code_position];
+        ++rank;
+    }
+}
+
+// one thread per job: the first interval_count - 1 markers must be RSTm with m = index mod 8; the last one ends the scan
+__global__ void k_decode_finish(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
+                                const uint32_t* __restrict__ marker_totals, const uint8_t* __restrict__ marker_codes,
+                                uint32_t job_count)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= job_count)
+        return;
+    const ScanJob& job = jobs[j];
+    const uint32_t found = marker_totals[j];
+    const uint8_t* codes = marker_codes + static_cast<size_t>(j) * p.interval_count;
+    for (uint32_t i = 0; i + 1 < p.interval_count; ++i)
+    {
+        if (i >= found)
+        {
+            report_error(job, i, err_need_more_data);
+            break;
+        }
+        if (codes[i] != 0xD0U + (i & 7U)) // reference src/scan_decoder.hpp:335-349
+        {
+            report_error(job, i, err_restart_marker_not_found);
+            break;
+        }
+    }
+    if (found < p.interval_count)
+    {
+        report_error(job, found, err_need_more_data);
+        job.result[0] = job.stream_in_size;
+    }
+    else
+    {
+        job.result[0] = job.interval_offset[2 * static_cast<size_t>(p.interval_count - 1) + 1];
+        job.result[1] = codes[p.interval_count - 1]; // the marker that closes the scan (EOI, SOS, DNL, ...)
+    }
+}
+
+__global__ void k_init_decode_tables(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * p.interval_count)
+        job.interval_offset[i] = ~0ULL;
+}
+
+__global__ void k_init_status(const ScanJob* __restrict__ jobs, uint32_t job_count)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < job_count)
+    {
+        *reinterpret_cast<unsigned long long*>(jobs[j].status) = ~0ULL;
+        jobs[j].result[0] = 0;
+        jobs[j].result[1] = 0;
+    }
+}
+
+// Batch encode: completes every frame's stream: header bytes in front of the entropy-coded data, EOI behind it.
+// One warp per frame.  stream_out points at the first entropy byte, i.e. header_size bytes into the frame's stream.
+__global__ void k_wrap_frames(const ScanJob* __restrict__ jobs, const uint8_t* __restrict__ header, uint32_t header_size,
+                              uint32_t job_count)
+{
+    const uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (j >= job_count)
+        return;
+    const ScanJob& job = jobs[j];
+    if (job.result[0] > job.stream_out_capacity)
+        return;
+    uint8_t* begin = job.stream_out - header_size;
+    for (uint32_t i = lane; i < header_size; i += 32)
+        begin[i] = header[i];
+    if (lane == 0)
+    {
+        job.stream_out[job.result[0]] = 0xFF;
+        job.stream_out[job.result[0] + 1] = 0xD9;
+    }
+}
+
+// Batch decode: gathers the first `prefix_bytes` of every stream so that the host can parse the headers with one copy.
+__global__ void k_copy_prefixes(const uint8_t* const* __restrict__ streams, const size_t* __restrict__ sizes,
+                                uint8_t* __restrict__ prefixes, uint32_t prefix_bytes, uint32_t job_count)
+{
+    const uint32_t j = blockIdx.x;
+    if (j >= job_count)
+        return;
+    const size_t n = sizes[j] < prefix_bytes ? sizes[j] : prefix_bytes;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x)
+        prefixes[static_cast<size_t>(j) * prefix_bytes + i] = streams[j][i];
+}
+
+template<typename Kernel, typename... Args>
+cudaError_t launch(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, Args... args)
+{
+    kernel<<<grid, block, 0, stream>>>(args...);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+uint64_t kernel_launch_count() noexcept
+{
+    return g_kernel_launches.load(std::memory_order_relaxed);
+}
+
+size_t marker_blocks_for(size_t stream_bytes) noexcept
+{
+    return (stream_bytes + marker_bytes_per_block - 1) / marker_bytes_per_block;
+}
+
+#define JLS_TRY(expr)                                                                                                  \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const cudaError_t jls_try_error = (expr);                                                                      \
+        if (jls_try_error != cudaSuccess)                                                                              \
+            return jls_try_error;                                                                                      \
+    } while (0)
+
+cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
+                          cudaStream_t stream)
+{
+    JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
+    const bool lossless = p.near == 0;
+    if (use_fast_path(p))
+    {
+        const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
+        const dim3 block(fast_block_threads);
+        if (p.interleave == ilv_sample)
+        {
+            if (lossless)
+                JLS_TRY(launch(k_encode_fast<3, true>, grid, block, stream, p, device_jobs, slot_bytes));
+            else
+                JLS_TRY(launch(k_encode_fast<3, false>, grid, block, stream, p, device_jobs, slot_bytes));
+        }
+        else
+        {
+            if (lossless)
+                JLS_TRY(launch(k_encode_fast<1, true>, grid, block, stream, p, device_jobs, slot_bytes));
+            else
+                JLS_TRY(launch(k_encode_fast<1, false>, grid, block, stream, p, device_jobs, slot_bytes));
+        }
+    }
+    else
+    {
+        const dim3 grid((p.interval_count + general_block_threads - 1) / general_block_threads, job_count);
+        if (lossless)
+            JLS_TRY(launch(k_encode_general<true>, grid, dim3(general_block_threads), stream, p, device_jobs, slot_bytes));
+        else
+            JLS_TRY(launch(k_encode_general<false>, grid, dim3(general_block_threads), stream, p, device_jobs, slot_bytes));
+    }
+    JLS_TRY(launch(k_scan_offsets, dim3(job_count), dim3(scan_block_threads), stream, p, device_jobs));
+    const dim3 gather_grid((p.interval_count + gather_block_threads / 32 - 1) / (gather_block_threads / 32), job_count);
+    JLS_TRY(launch(k_gather, gather_grid, dim3(gather_block_threads), stream, p, device_jobs, slot_bytes));
+    return cudaSuccess;
+}
+
+cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
+                          uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream)
+{
+    const uint32_t blocks_per_job = static_cast<uint32_t>(marker_blocks_for(max_stream_bytes));
+    JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
+    JLS_TRY(launch(k_init_decode_tables, dim3((2 * p.interval_count + 255) / 256, job_count), dim3(256), stream, p,
+                   device_jobs));
+    JLS_TRY(launch(k_marker_count, dim3(blocks_per_job, job_count), dim3(marker_block_threads), stream, device_jobs,
+                   block_counts, blocks_per_job));
+    JLS_TRY(launch(k_marker_scan, dim3(job_count), dim3(scan_block_threads), stream, block_counts, blocks_per_job,
+                   marker_totals));
+    JLS_TRY(launch(k_marker_write, dim3(blocks_per_job, job_count), dim3(marker_block_threads), stream, p, device_jobs,
+                   static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes));
+
+    const bool lossless = p.near == 0;
+    if (use_fast_path(p))
+    {
+        const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
+        const dim3 block(fast_block_threads);
+        if (p.interleave == ilv_sample)
+        {
+            if (lossless)
+                JLS_TRY(launch(k_decode_fast<3, true>, grid, block, stream, p, device_jobs));
+            else
+                JLS_TRY(launch(k_decode_fast<3, false>, grid, block, stream, p, device_jobs));
+        }
+        else
+        {
+            if (lossless)
+                JLS_TRY(launch(k_decode_fast<1, true>, grid, block, stream, p, device_jobs));
+            else
+                JLS_TRY(launch(k_decode_fast<1, false>, grid, block, stream, p, device_jobs));
+        }
+    }
+    else
+    {
+        const dim3 grid((p.interval_count + general_block_threads - 1) / general_block_threads, job_count);
+        if (lossless)
+            JLS_TRY(launch(k_decode_general<true>, grid, dim3(general_block_threads), stream, p, device_jobs));
+        else
+            JLS_TRY(launch(k_decode_general<false>, grid, dim3(general_block_threads), stream, p, device_jobs));
+    }
+    JLS_TRY(launch(k_decode_finish, dim3((job_count + 127) / 128), dim3(128), stream, p, device_jobs,
+                   static_cast<const uint32_t*>(marker_totals), static_cast<const uint8_t*>(marker_codes), job_count));
+    return cudaSuccess;
+}
+
+cudaError_t launch_wrap_frames(const ScanJob* device_jobs, const uint8_t* device_header, uint32_t header_size,
+                               uint32_t job_count, cudaStream_t stream)
+{
+    return launch(k_wrap_frames, dim3((job_count + 3) / 4), dim3(128), stream, device_jobs, device_header, header_size,
+                  job_count);
+}
+
+cudaError_t launch_copy_prefixes(const uint8_t* const* device_streams, const size_t* device_sizes, uint8_t* device_prefixes,
+                                 uint32_t prefix_bytes, uint32_t job_count, cudaStream_t stream)
+{
+    return launch(k_copy_prefixes, dim3(job_count), dim3(128), stream, device_streams, device_sizes, device_prefixes,
+                  prefix_bytes, job_count);
+}
+
+} // namespace jls

@@ -1,0 +1,35 @@
+// jls_kernels.hpp -- launch wrappers of the sm_100a kernels (implemented in jls_kernels.cu).
+#pragma once
+
+#include "jls_common.h"
+
+#include <atomic>
+#include <cuda_runtime_api.h>
+
+namespace jls {
+
+// Number of kernels this library has launched in this process (evidence for bench.py's "gpu_launches").
+uint64_t kernel_launch_count() noexcept;
+
+// Blocks (of 4096 stream bytes) the marker kernels use for a stream of `stream_bytes`.
+size_t marker_blocks_for(size_t stream_bytes) noexcept;
+
+// Encodes `job_count` scans that share the coding parameters `p`.  Afterwards, per job: result[0] = bytes written to
+// stream_out (interval data + RSTm markers), status = first error key (~0 when none).
+cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
+                          cudaStream_t stream);
+
+// Decodes `job_count` scans.  block_counts: job_count * marker_blocks_for(max_stream_bytes) uint32; marker_totals:
+// job_count uint32; marker_codes: job_count * interval_count bytes.  Afterwards result[0] = bytes consumed by the scan.
+cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
+                          uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream);
+
+// Batch encode: writes `header` in front of and EOI behind every frame's entropy-coded data (see k_wrap_frames).
+cudaError_t launch_wrap_frames(const ScanJob* device_jobs, const uint8_t* device_header, uint32_t header_size,
+                               uint32_t job_count, cudaStream_t stream);
+
+// Batch decode: prefixes[j * prefix_bytes ...] = first bytes of stream j.
+cudaError_t launch_copy_prefixes(const uint8_t* const* device_streams, const size_t* device_sizes, uint8_t* device_prefixes,
+                                 uint32_t prefix_bytes, uint32_t job_count, cudaStream_t stream);
+
+} // namespace jls
