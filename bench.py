@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- MPixels/s of the JPEG-LS scan engine (encode + decode), HBM roofline fraction, CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU codec on the box's host cores
+
+One *step* = encode + decode of `--frames` synthetic frames per GPU with restart interval 1 (every line an independent
+work item).  Frames and streams are resident in HBM when the timed region starts (`value`); `e2e` measures the same
+round trip through the reference-facing C ABI (charls_jpegls_encoder_encode_from_buffer /
+charls_jpegls_decoder_decode_to_buffer) with pinned HOST buffers, copies included.
+Multi GPU (torchrun): frames are sharded across ranks, no data-path collective; NCCL only all-gathers the stream sizes.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, bits, components, near, interleave, transform)
+    "cfg2": (4096, 4096, 8, 1, 0, 0, 0),   # BASELINE.json configs[1]: 4096x4096 8-bit grayscale lossless
+    "cfg3": (4096, 4096, 12, 1, 2, 0, 0),  # configs[2]: 12-bit NEAR=2
+    "cfg4": (2048, 2048, 16, 3, 0, 2, 1),  # configs[3]: 16-bit RGB, ILV sample, HP1
+}
+METRIC = "MPixels/s encode+decode"
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcharls_ref.so")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step (128 x 8 GPUs = BASELINE configs[4])")
+    ap.add_argument("--e2e-frames", type=int, default=16)
+    ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic frames: S_smooth of SURVEY.md 8(d) -- smooth base + 1% gaussian noise, generated on the device
+# ---------------------------------------------------------------------------------------------------------------------
+def make_frames(torch, device, count, workload, first_seed):
+    w, h, bits, cc, _, ilv, _ = WORKLOADS[workload]
+    mx = (1 << bits) - 1
+    x = torch.arange(w, device=device, dtype=torch.float32)[None, :]
+    y = torch.arange(h, device=device, dtype=torch.float32)[:, None]
+    base = 0.8 * mx * (0.5 + 0.25 * torch.sin(x / 97.0) + 0.25 * torch.cos(y / 131.0))
+    dtype = torch.uint8 if bits <= 8 else torch.int16  # int16 carries the uint16 bit pattern
+    shape = (count, h, w) if cc == 1 else (count, h, w, cc)
+    frames = torch.empty(shape, device=device, dtype=dtype)
+    gen = torch.Generator(device=device)
+    for i in range(count):
+        gen.manual_seed(first_seed + i)
+        for c in range(cc):
+            noise = torch.randn((h, w), device=device, generator=gen) * (0.01 * mx)
+            v = torch.clamp(base * (1 - 0.1 * c) + noise, 0, mx).to(torch.int32)
+            if bits > 8:
+                v = torch.where(v > 32767, v - 65536, v)
+            if cc == 1:
+                frames[i] = v.to(dtype)
+            else:
+                frames[i, :, :, c] = v.to(dtype)
+    return frames
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the UNMODIFIED reference (oracle/_ref) on the host cores, one frame per thread
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(ref, frames_np, workload, threads):
+    """Encodes and decodes frames_np[i] on `threads` host threads with the reference library. Returns seconds."""
+    from charls_b200 import codec
+
+    w, h, bits, cc, near, ilv, xf = WORKLOADS[workload]
+
+    def work(i):
+        s = codec.encode(frames_np[i], bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf, lib=ref)
+        px, _, _ = codec.decode(s, lib=ref)
+        return len(s)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(work, range(len(frames_np))))
+    return time.perf_counter() - t0
+
+
+def host_frames(workload, count, seed=1234):
+    """numpy S_smooth frames for the CPU arm (cheap generator shared by `count` frames with different noise)."""
+    w, h, bits, cc, _, _, _ = WORKLOADS[workload]
+    mx = (1 << bits) - 1
+    x = np.arange(w, dtype=np.float32)[None, :]
+    y = np.arange(h, dtype=np.float32)[:, None]
+    base = 0.8 * mx * (0.5 + 0.25 * np.sin(x / 97.0) + 0.25 * np.cos(y / 131.0))
+    dtype = np.uint8 if bits <= 8 else np.dtype("<u2")
+    out = []
+    for i in range(count):
+        rng = np.random.default_rng(seed + i)
+        comps = [np.clip(base * (1 - 0.1 * c) + rng.standard_normal((h, w), dtype=np.float32) * (0.01 * mx), 0, mx).astype(dtype)
+                 for c in range(cc)]
+        out.append(comps[0] if cc == 1 else np.stack(comps, axis=-1))
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
+    if not os.path.exists(REF_LIB):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcharls_ref.so was not built (run __graft_entry__.build() where /root/reference exists)"}))
+        return
+    from charls_b200.capi import CharlsLibrary
+
+    ref = CharlsLibrary(REF_LIB, extensions=False)
+    threads = os.cpu_count() or 1
+    frames = host_frames(args.workload, min(threads, 8))
+    frames = [frames[i % len(frames)] for i in range(threads)]  # one frame per thread per step
+    for _ in range(args.warmup):
+        cpu_reference_step(ref, frames, args.workload, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference_step(ref, frames, args.workload, threads)
+    pixels = threads * w * h * args.steps
+    value = pixels / t / 1e6
+    sample = f"{threads} host threads x 1 frame of {args.workload} per step (reference encode, no restart markers, + decode of its own stream)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if bits <= 8 else "u16", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_step": threads},
+        "cpu_baseline": {"value": value, "unit": "MPixels/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(args):
+    w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
+    return (f"{args.workload}: {w}x{h} {bits}-bit x{cc} NEAR={near} ILV={ilv} HP{xf} restart-interval=1, "
+            f"{args.frames} frames per GPU per step")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads):
+    """Through the C ABI with pinned host buffers: every frame encoded, then every stream decoded. Returns (s, sizes)."""
+    from charls_b200.capi import FrameInfo
+
+    w, h, bits, cc, near, ilv, xf = WORKLOADS[workload]
+    n = frames_host.shape[0]
+    sizes = [0] * n
+    frame_bytes = frames_host[0].numel() * frames_host.element_size()
+    cap = streams_host.shape[1]
+
+    def enc(i):
+        e = lib.charls_jpegls_encoder_create()
+        fi = FrameInfo(w, h, bits, cc)
+        lib.check(lib.charls_jpegls_encoder_set_frame_info(e, C.byref(fi)))
+        lib.check(lib.charls_jpegls_encoder_set_near_lossless(e, near))
+        lib.check(lib.charls_jpegls_encoder_set_interleave_mode(e, ilv))
+        lib.check(lib.charls_jpegls_encoder_set_color_transformation(e, xf))
+        lib.check(lib.charls_jpegls_encoder_set_destination_buffer(e, streams_host[i].data_ptr(), cap))
+        lib.check(lib.charls_jpegls_encoder_encode_from_buffer(e, frames_host[i].data_ptr(), frame_bytes, 0))
+        written = C.c_size_t()
+        lib.check(lib.charls_jpegls_encoder_get_bytes_written(e, C.byref(written)))
+        lib.charls_jpegls_encoder_destroy(e)
+        sizes[i] = written.value
+
+    def dec(i):
+        d = lib.charls_jpegls_decoder_create()
+        lib.check(lib.charls_jpegls_decoder_set_source_buffer(d, streams_host[i].data_ptr(), sizes[i]))
+        lib.check(lib.charls_jpegls_decoder_read_header(d))
+        lib.check(lib.charls_jpegls_decoder_decode_to_buffer(d, out_host[i].data_ptr(), frame_bytes, 0))
+        lib.charls_jpegls_decoder_destroy(d)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(enc, range(n)))
+        list(pool.map(dec, range(n)))
+    return time.perf_counter() - t0, sizes
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from charls_b200 import capi
+    from charls_b200.batch import BatchCodec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    lib = capi.default_library()
+    lib.check(lib.charlsx_set_device(local_rank))
+    w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
+    F = args.frames
+    frames = make_frames(torch, device, F, args.workload, first_seed=1234 + rank * F)
+    codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=1, lib=lib)
+    streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
+    decoded = torch.empty_like(frames)
+    raw_bytes = frames[0].numel() * frames.element_size()
+
+    def step():
+        sizes = codec.encode(frames, streams)
+        t_enc = codec.last_coder_kernel_ms()
+        codec.decode(streams, sizes, decoded)
+        t_dec = codec.last_coder_kernel_ms()
+        return sizes, t_enc, t_dec
+
+    for _ in range(max(args.warmup, 3)):
+        sizes, _, _ = step()
+    torch.cuda.synchronize()
+
+    # parity spot check outside the timed region: the round trip must reproduce the frames (within NEAR)
+    if near == 0:
+        assert torch.equal(decoded, frames), "round trip mismatch"
+    else:
+        a = decoded.to(torch.int32) & 0xFFFF if bits > 8 else decoded.to(torch.int32)
+        b = frames.to(torch.int32) & 0xFFFF if bits > 8 else frames.to(torch.int32)
+        assert int((a - b).abs().max()) <= near, "near-lossless bound violated"
+
+    launches_before = C.c_uint64()
+    lib.check(lib.charlsx_get_kernel_launch_count(C.byref(launches_before)))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    enc_ms, dec_ms = [], []
+    for _ in range(args.steps):
+        sizes, t_enc, t_dec = step()
+        enc_ms.append(t_enc)
+        dec_ms.append(t_dec)
+    stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches_after = C.c_uint64()
+    lib.check(lib.charlsx_get_kernel_launch_count(C.byref(launches_after)))
+
+    elapsed_ms = torch.tensor([start.elapsed_time(stop)], device=device, dtype=torch.float64)
+    comp_total = torch.tensor([float(sum(sizes))], device=device, dtype=torch.float64)
+    kernel_ms = torch.tensor([float(np.mean(enc_ms)), float(np.mean(dec_ms))], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
+        # control plane only: every rank learns every frame's stream size (the global offset table of the batch)
+        gathered = [torch.empty(F, device=device, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor(sizes, device=device, dtype=torch.int64))
+        comp_total = torch.stack(gathered).sum().to(torch.float64).reshape(1)
+    else:
+        comp_total = comp_total
+
+    ms_per_step = float(elapsed_ms.item()) / args.steps
+    pixels_per_step = world * F * w * h
+    value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
+    comp_per_frame = float(comp_total.item()) / (world * F)
+
+    # ---- e2e through the C ABI with pinned host buffers (rank-local, then summed)
+    e2e = None
+    if not args.no_e2e:
+        n = min(args.e2e_frames, F)
+        frames_host = torch.empty((n,) + tuple(frames.shape[1:]), dtype=frames.dtype, pin_memory=True)
+        frames_host.copy_(frames[:n])
+        streams_host = torch.empty((n, codec.stream_capacity), dtype=torch.uint8, pin_memory=True)
+        out_host = torch.empty_like(frames_host, pin_memory=True)
+        torch.cuda.synchronize()
+        threads = max(1, min(args.e2e_threads, os.cpu_count() or 1))
+        for _ in range(3):
+            e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads)
+        if world > 1:
+            dist.barrier()
+        t_e2e, e2e_sizes = 0.0, None
+        reps = max(3, args.steps)
+        for _ in range(reps):
+            dt, e2e_sizes = e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads)
+            t_e2e += dt
+        if near == 0:
+            assert torch.equal(out_host, frames_host), "e2e round trip mismatch"
+        t = torch.tensor([t_e2e / reps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        comp = sum(e2e_sizes)
+        e2e = {
+            "value": world * n * w * h / float(t.item()) / 1e6, "unit": "MPixels/s",
+            "h2d_bytes_per_step": world * (n * raw_bytes + comp), "d2h_bytes_per_step": world * (comp + n * raw_bytes),
+            "frames_per_step": world * n, "host_threads": threads,
+            "api": "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
+        }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the entropy-coding kernels (algorithmic bytes = raw + compressed)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_kind = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_kind = 6650.0, "fallback (B200_PROFILING.md)"
+    algorithmic = F * (raw_bytes + comp_per_frame)
+    t_enc, t_dec = float(kernel_ms[0].item()), float(kernel_ms[1].item())
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+
+    def roof(name, ms):
+        achieved = algorithmic / (ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get(f"{name}:{args.workload}:{F}"), "ms_per_launch": ms, "peak_source": peak_kind,
+                "algorithmic_bytes_per_launch": algorithmic}
+
+    fast = "k_encode_fast" if True else ""
+    roofs = {"encode": roof("k_encode_fast", t_enc), "decode": roof("k_decode_fast", t_dec)}
+    dominant = roofs["encode"] if t_enc >= t_dec else roofs["decode"]
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu and os.path.exists(REF_LIB):
+        ref = capi.CharlsLibrary(REF_LIB, extensions=False)
+        threads = os.cpu_count() or 1
+        hf = host_frames(args.workload, min(threads, 4))
+        hf = [hf[i % len(hf)] for i in range(threads)]
+        cpu_reference_step(ref, hf, args.workload, threads)  # warm
+        reps, t = 0, 0.0
+        while t < 6.0 and reps < 20:
+            t += cpu_reference_step(ref, hf, args.workload, threads)
+            reps += 1
+        cpu_baseline = {"value": threads * reps * w * h / t / 1e6, "unit": "MPixels/s", "cores": threads, "kind": "reference",
+                        "sample": f"{threads} threads x {reps} frames of {args.workload}: unmodified reference encode (no restart markers) + decode"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "MPixels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if bits <= 8 else "u16", "data": "synthetic",
+        "config": {"workload": workload_name(args), "frames_per_step": world * F, "restart_interval": 1,
+                   "compressed_bytes_per_frame": comp_per_frame, "ratio": raw_bytes / comp_per_frame,
+                   "cache": f"inputs larger than L2: {F * raw_bytes / 1e6:.0f} MB raw + {F * comp_per_frame / 1e6:.0f} MB streams per GPU vs 126 MB L2",
+                   "sharding": "frames split across ranks, no data-path collective; NCCL all_gather of stream sizes only"},
+        "encode_mpix_s": world * F * w * h / (t_enc * 1e-3) / 1e6, "decode_mpix_s": world * F * w * h / (t_dec * 1e-3) / 1e6,
+        "roofline": dominant, "roofline_all": roofs, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": int(launches_after.value - launches_before.value),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

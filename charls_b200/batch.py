@@ -1,0 +1,82 @@
+"""Device-resident batch interface (charlsx_batch_*): frames and streams stay in HBM, only headers cross PCIe.
+
+PyTorch is used for what it is good at here -- device memory and streams; the codec itself is the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from ctypes import byref
+
+from .capi import BatchImage, BatchParams, CharlsLibrary, FrameInfo, default_library
+
+
+class BatchCodec:
+    """Encodes / decodes batches of equally shaped frames that live in CUDA tensors."""
+
+    def __init__(self, width, height, bits_per_sample, component_count=1, *, near_lossless=0, interleave_mode=0,
+                 color_transformation=0, restart_interval=1, lib: CharlsLibrary | None = None):
+        self.lib = lib or default_library()
+        self.params = BatchParams(
+            FrameInfo(width, height, bits_per_sample, component_count), near_lossless, interleave_mode, color_transformation,
+            restart_interval, 0, 0,
+        )
+        self._h = self.lib.charlsx_batch_create()
+        if not self._h:
+            raise MemoryError("charlsx_batch_create failed")
+        sample_bytes = 1 if bits_per_sample <= 8 else 2
+        self.frame_bytes = width * height * component_count * sample_bytes
+        # same bound the single-image encoder reports (reference formula + restart-marker overhead)
+        intervals = (height + restart_interval - 1) // restart_interval if restart_interval else 0
+        self.stream_capacity = self.frame_bytes + self.frame_bytes // 16 + 1024 + 34 + 4 * intervals + 8
+        self.stream_capacity = (self.stream_capacity + 255) // 256 * 256
+
+    def close(self):
+        if self._h:
+            self.lib.charlsx_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _images(self, pixels, streams, sizes):
+        n = pixels.shape[0]
+        images = (BatchImage * n)()
+        pixel_stride = pixels.stride(0) * pixels.element_size()
+        stream_stride = streams.stride(0) * streams.element_size()
+        p0, s0 = pixels.data_ptr(), streams.data_ptr()
+        for i in range(n):
+            images[i].pixels = p0 + i * pixel_stride
+            images[i].stream = s0 + i * stream_stride
+            images[i].stream_capacity = stream_stride if sizes is None else int(sizes[i])
+        return images
+
+    @staticmethod
+    def _stream_handle(stream):
+        if stream is None:
+            import torch
+
+            stream = torch.cuda.current_stream()
+        return C.c_void_p(stream.cuda_stream)
+
+    def encode(self, pixels, streams, stream=None):
+        """pixels: CUDA tensor [N, ...frame]; streams: CUDA uint8 tensor [N, capacity].  Returns list of stream sizes."""
+        images = self._images(pixels, streams, None)
+        errc = self.lib.charlsx_batch_encode(self._h, byref(self.params), images, len(images), self._stream_handle(stream))
+        self.lib.check(errc)
+        return [images[i].stream_size for i in range(len(images))]
+
+    def decode(self, streams, sizes, pixels, stream=None):
+        """streams: CUDA uint8 tensor [N, capacity] holding complete JPEG-LS streams of `sizes` bytes; pixels: output."""
+        images = self._images(pixels, streams, sizes)
+        errc = self.lib.charlsx_batch_decode(self._h, byref(self.params), images, len(images), self._stream_handle(stream))
+        self.lib.check(errc)
+        return [images[i].stream_size for i in range(len(images))]
+
+    def last_coder_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self.lib.check(self.lib.charlsx_batch_get_last_coder_kernel_ms(self._h, byref(ms)))
+        return ms.value
+
+    def last_kernel_launches(self) -> int:
+        n = C.c_uint32()
+        self.lib.check(self.lib.charlsx_batch_get_last_kernel_launches(self._h, byref(n)))
+        return n.value

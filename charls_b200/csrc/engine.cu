@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
 
 namespace jls {
 
@@ -81,8 +83,55 @@ Engine::~Engine()
                       &outcomes_, &marker_counts_, &marker_totals_, &marker_codes_, &header_, &pointer_table_, &prefixes_,
                       &host_outcomes_, &host_jobs_, &host_prefixes_, &host_pointer_table_})
         release(*b);
+    for (auto& event : events_)
+        if (event)
+            cudaEventDestroy(event);
     if (stream_)
         cudaStreamDestroy(stream_);
+}
+
+namespace {
+std::mutex g_pool_mutex;
+std::vector<Engine*> g_pool;
+constexpr size_t pool_limit = 64;
+} // namespace
+
+Engine* Engine::acquire()
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!g_pool.empty())
+        {
+            Engine* engine = g_pool.back();
+            g_pool.pop_back();
+            return engine;
+        }
+    }
+    return new Engine;
+}
+
+void Engine::release(Engine* engine) noexcept
+{
+    if (!engine)
+        return;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (g_pool.size() < pool_limit && (g_device.load() < 0 || engine->device_ < 0 || engine->device_ == g_device.load()))
+        {
+            g_pool.push_back(engine);
+            return;
+        }
+    }
+    delete engine;
+}
+
+void Engine::read_coder_time() noexcept
+{
+    float ms = 0.0F;
+    if (cudaEventElapsedTime(&ms, events_[0], events_[1]) == cudaSuccess)
+        last_coder_ms_ = ms;
+    else
+        cudaGetLastError();
 }
 
 void Engine::release(Buffer& buffer) noexcept
@@ -110,6 +159,9 @@ int32_t Engine::prepare()
     device_ = wanted;
     if (!stream_)
         JLS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& event : events_)
+        if (!event)
+            JLS_CUDA(cudaEventCreate(&event));
     return 0;
 }
 
@@ -206,8 +258,9 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     jobs[0].stream_out = static_cast<uint8_t*>(stream_buffer_.data);
     jobs[0].stream_out_capacity = device_capacity;
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_));
-    JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_));
+    JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, events_));
     JLS_CHECK(fetch_outcomes(1, stream_));
+    read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
 
     const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
@@ -260,8 +313,9 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream_));
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), 1, remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                           static_cast<uint8_t*>(marker_codes_.data), stream_));
+                           static_cast<uint8_t*>(marker_codes_.data), stream_, events_));
     JLS_CHECK(fetch_outcomes(1, stream_));
+    read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
 
     const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
@@ -305,10 +359,11 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     }
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream));
     const ScanJob* device_jobs = static_cast<const ScanJob*>(job_table_.data);
-    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream));
+    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream, events_));
     JLS_CUDA(launch_wrap_frames(device_jobs, static_cast<const uint8_t*>(header_.data), static_cast<uint32_t>(header_size),
                                 static_cast<uint32_t>(count), stream));
     JLS_CHECK(fetch_outcomes(count, stream));
+    read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
 
     int32_t first_error = 0;
@@ -382,8 +437,9 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream));
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), static_cast<uint32_t>(count), max_remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                           static_cast<uint8_t*>(marker_codes_.data), stream));
+                           static_cast<uint8_t*>(marker_codes_.data), stream, events_));
     JLS_CHECK(fetch_outcomes(count, stream));
+    read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
 
     int32_t first_error = 0;

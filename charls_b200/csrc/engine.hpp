@@ -15,6 +15,7 @@
 #include <vector>
 
 struct CUstream_st;
+struct CUevent_st;
 
 namespace jls {
 
@@ -64,6 +65,13 @@ public:
                               CUstream_st* user_stream);
 
     uint32_t last_kernel_launches() const noexcept { return last_launches_; }
+    // Device time (CUDA events on the launching stream) of the entropy-coding kernel of the last call, in milliseconds.
+    float last_coder_kernel_ms() const noexcept { return last_coder_ms_; }
+
+    // Engines are pooled: an encoder / decoder object borrows one for its lifetime, so that programs that create a
+    // codec object per image (the usual way to use the reference API) do not pay for device allocations every time.
+    static Engine* acquire();
+    static void release(Engine* engine) noexcept;
 
 private:
     struct Buffer
@@ -79,6 +87,7 @@ private:
     // Lays out the per-job scratch for `job_count` jobs and uploads the job table. Scratch pointers are filled in here.
     int32_t stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream);
     int32_t fetch_outcomes(size_t job_count, CUstream_st* stream);
+    void read_coder_time() noexcept;
 
     CUstream_st* stream_{};
     int device_{-1};
@@ -87,6 +96,8 @@ private:
     Buffer host_outcomes_, host_jobs_, host_prefixes_, host_pointer_table_; // pinned
     size_t uploaded_stream_size_{};
     uint32_t last_launches_{};
+    float last_coder_ms_{};
+    CUevent_st* events_[2]{};
 };
 
 } // namespace jls

@@ -203,6 +203,11 @@ charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batc
     });
 }
 
+charls_jpegls_errc charlsx_batch_get_last_coder_kernel_ms(const charlsx_batch* batch, float* milliseconds) noexcept
+{
+    return guarded([&] { *check_pointer(milliseconds) = check_pointer(batch)->engine.last_coder_kernel_ms(); });
+}
+
 charls_jpegls_errc charlsx_batch_get_last_kernel_launches(const charlsx_batch* batch, uint32_t* launches) noexcept
 {
     return guarded([&] { *check_pointer(launches) = check_pointer(batch)->engine.last_kernel_launches(); });

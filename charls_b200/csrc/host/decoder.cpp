@@ -12,6 +12,14 @@ using namespace jls::host;
 
 struct charls_jpegls_decoder final
 {
+    ~charls_jpegls_decoder() { Engine::release(engine_); }
+    Engine& engine()
+    {
+        if (!engine_)
+            engine_ = Engine::acquire();
+        return *engine_;
+    }
+
     enum class State
     {
         initial,
@@ -113,7 +121,7 @@ struct charls_jpegls_decoder final
         check_buffer(destination, destination_size);
         check_operation(state_ == State::header_read);
         const charls_frame_info& info = reader_.frame_info();
-        check_status(engine_.upload_stream(reader_.source_data(), reader_.source_size()));
+        check_status(engine().upload_stream(reader_.source_data(), reader_.source_size()));
 
         for (size_t component = 0;;)
         {
@@ -126,7 +134,7 @@ struct charls_jpegls_decoder final
                                                     reader_.scan_near_lossless(), ilv, ilv != 0 ? reader_.color_transformation() : 0,
                                                     preset, reader_.restart_interval());
             size_t consumed = 0;
-            check_status(engine_.decode_scan_to_host(p, reader_.position(), destination, scan_stride, consumed));
+            check_status(engine().decode_scan_to_host(p, reader_.position(), destination, scan_stride, consumed));
             reader_.advance(consumed);
 
             component += reader_.scan_component_count();
@@ -165,7 +173,7 @@ private:
 
     State state_{State::initial};
     StreamReader reader_;
-    Engine engine_;
+    Engine* engine_{}; // borrowed from the pool on first use
 };
 
 extern "C" {

@@ -14,6 +14,14 @@ using namespace jls::host;
 
 struct charls_jpegls_encoder final
 {
+    ~charls_jpegls_encoder() { Engine::release(engine_); }
+    Engine& engine()
+    {
+        if (!engine_)
+            engine_ = Engine::acquire();
+        return *engine_;
+    }
+
     enum class State
     {
         initial,
@@ -298,7 +306,7 @@ private:
                                                 frame_info_.bits_per_sample, component_count, near_lossless_, interleave_mode_,
                                                 interleave_mode_ != 0 ? color_transformation_ : 0, preset_, restart_interval_);
         size_t written = 0;
-        check_status(engine_.encode_scan_from_host(p, source, stride, writer_.remaining_data(), writer_.remaining_size(), written));
+        check_status(engine().encode_scan_from_host(p, source, stride, writer_.remaining_data(), writer_.remaining_size(), written));
         writer_.advance(written);
     }
 
@@ -319,7 +327,7 @@ private:
     StreamWriter writer_;
     charls_jpegls_pc_parameters user_preset_{};
     PresetCodingParameters preset_{};
-    Engine engine_;
+    Engine* engine_{}; // borrowed from the pool on first use
 };
 
 extern "C" {

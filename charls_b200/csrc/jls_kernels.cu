@@ -446,10 +446,12 @@ size_t marker_blocks_for(size_t stream_bytes) noexcept
     } while (0)
 
 cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
-                          cudaStream_t stream)
+                          cudaStream_t stream, cudaEvent_t* coder_events)
 {
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
     const bool lossless = p.near == 0;
+    if (coder_events)
+        JLS_TRY(cudaEventRecord(coder_events[0], stream));
     if (use_fast_path(p))
     {
         const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
@@ -477,6 +479,8 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
         else
             JLS_TRY(launch(k_encode_general<false>, grid, dim3(general_block_threads), stream, p, device_jobs, slot_bytes));
     }
+    if (coder_events)
+        JLS_TRY(cudaEventRecord(coder_events[1], stream));
     JLS_TRY(launch(k_scan_offsets, dim3(job_count), dim3(scan_block_threads), stream, p, device_jobs));
     const dim3 gather_grid((p.interval_count + gather_block_threads / 32 - 1) / (gather_block_threads / 32), job_count);
     JLS_TRY(launch(k_gather, gather_grid, dim3(gather_block_threads), stream, p, device_jobs, slot_bytes));
@@ -484,7 +488,8 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
 }
 
 cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
-                          uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream)
+                          uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream,
+                          cudaEvent_t* coder_events)
 {
     const uint32_t blocks_per_job = static_cast<uint32_t>(marker_blocks_for(max_stream_bytes));
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
@@ -498,6 +503,8 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
                    static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes));
 
     const bool lossless = p.near == 0;
+    if (coder_events)
+        JLS_TRY(cudaEventRecord(coder_events[0], stream));
     if (use_fast_path(p))
     {
         const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
@@ -525,6 +532,8 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
         else
             JLS_TRY(launch(k_decode_general<false>, grid, dim3(general_block_threads), stream, p, device_jobs));
     }
+    if (coder_events)
+        JLS_TRY(cudaEventRecord(coder_events[1], stream));
     JLS_TRY(launch(k_decode_finish, dim3((job_count + 127) / 128), dim3(128), stream, p, device_jobs,
                    static_cast<const uint32_t*>(marker_totals), static_cast<const uint8_t*>(marker_codes), job_count));
     return cudaSuccess;

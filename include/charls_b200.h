@@ -371,6 +371,9 @@ CHARLS_B200_API charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, co
                                                         charlsx_batch_image* images, size_t count, void* cuda_stream) CHARLS_B200_NOEXCEPT;
 /* Kernels launched by the last charlsx_batch_encode / _decode call on this object. */
 CHARLS_B200_API charls_jpegls_errc charlsx_batch_get_last_kernel_launches(const charlsx_batch* batch, uint32_t* launches) CHARLS_B200_NOEXCEPT;
+/* Device time (CUDA events on the launching stream, recorded directly around it) of the entropy-coding kernel of the
+   last charlsx_batch_encode / _decode call on this object, in milliseconds. */
+CHARLS_B200_API charls_jpegls_errc charlsx_batch_get_last_coder_kernel_ms(const charlsx_batch* batch, float* milliseconds) CHARLS_B200_NOEXCEPT;
 /* Kernels launched by this library in this process so far. */
 CHARLS_B200_API charls_jpegls_errc charlsx_get_kernel_launch_count(uint64_t* launches) CHARLS_B200_NOEXCEPT;
 

@@ -1,0 +1,294 @@
+"""GPU parity tests: everything goes through the C ABI of charls_b200/lib/libcharls.so.3 (CUDA kernels) and is compared
+bit-for-bit with the oracle, the committed golden vectors and -- its prebuilt .so travels with the repository -- the
+unmodified reference library."""
+import hashlib
+import threading
+
+import numpy as np
+import pytest
+
+from charls_b200 import capi, codec
+from charls_b200.capi import CharlsError
+from tests import jlsio
+from tests.golden_vectors import load_fixture_streams
+from tests.support import have_reference_build, reference_library, s_mixed, s_noise, s_smooth
+
+pytestmark = pytest.mark.gpu
+
+
+def payloads(stream):
+    s = jlsio.parse(stream)
+    return [stream[sc.data_offset : sc.data_end] for sc in s.scans]
+
+
+def encode(lib, image, bits, **kw):
+    """codec.encode with a destination big enough for incompressible input (the estimate is the reference's formula)."""
+    from charls_b200.codec import JpegLSEncoder, _shape_info
+
+    ilv = kw.get("interleave_mode", 0)
+    h, w, c = _shape_info(image, ilv)
+    with JpegLSEncoder(lib) as enc:
+        enc.frame_info(w, h, bits, c).near_lossless(kw.get("near_lossless", 0)).interleave_mode(ilv)
+        enc.color_transformation(kw.get("color_transformation", 0))
+        if kw.get("preset") is not None:
+            enc.preset_coding_parameters(*kw["preset"])
+        if kw.get("restart_interval") is not None and lib.has_extensions:
+            enc.restart_interval(kw["restart_interval"])
+        dst = np.empty(enc.estimated_destination_size() * 2 + 4096, dtype=np.uint8)
+        enc.destination(dst)
+        return dst[: enc.encode(image)].tobytes()
+
+
+def test_golden_vectors(product, golden):
+    """Reference-made vectors: Ri=1 output == streams stitched from the reference's per-row encodings, Ri=0 output ==
+    the reference's own encoding byte for byte, decoding either == the reference's decoding."""
+    for v in golden:
+        kw = dict(near_lossless=v.near, interleave_mode=v.ilv, color_transformation=v.xf, preset=v.pc)
+        assert payloads(encode(product, v.image, v.bits, restart_interval=1, **kw)) == payloads(v.ri1), v.name
+        assert payloads(encode(product, v.image, v.bits, restart_interval=0, **kw)) == payloads(v.ri0), v.name
+        for stream, want in ((v.ri0, v.dec0), (v.ri1, v.dec1)):
+            got, _, _ = codec.decode(stream, lib=product)
+            assert np.array_equal(got, want), v.name
+
+
+def test_reference_fixture_streams(product):
+    """The streams of the reference's own test-suite (restart intervals 5/7/300, Annex E, HP3, corrupt input):
+    same pixels or same error code as the reference (test/compliance_test.cpp:43-141, jpegls_decoder_test.cpp:836-901)."""
+    for name, stream, errc, digest, shape in load_fixture_streams():
+        if errc == 0:
+            got, _, _ = codec.decode(stream, lib=product)
+            assert got.shape == tuple(shape), name
+            assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == digest, name
+        else:
+            with pytest.raises(CharlsError) as info:
+                codec.decode(stream, lib=product)
+            assert info.value.errc == errc, name
+
+
+@pytest.mark.parametrize("bits", [2, 5, 8, 12, 16])
+def test_scalar_sweep_vs_oracle(product, oracle, bits):
+    for gen in (s_smooth, s_noise, s_mixed):
+        for (h, w) in ((9, 33), (1, 9), (13, 1), (70, 300)):
+            img = gen(h, w, bits)
+            for near in (0, 2):
+                if near > ((1 << bits) - 1) // 2:
+                    continue
+                for ri in (1, 0, 3):
+                    got = encode(product, img, bits, near_lossless=near, restart_interval=ri)
+                    want = oracle.encode_image(img, bits, near=near, ri=ri)
+                    assert payloads(got) == payloads(want), (gen.__name__, h, w, bits, near, ri)
+                    expected, _ = oracle.decode_image(got)
+                    px, _, _ = codec.decode(got, lib=product)
+                    assert np.array_equal(px, expected), (gen.__name__, h, w, bits, near, ri)
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_color_sweep_vs_oracle(product, oracle, bits):
+    for cc in (2, 3, 4):
+        for ilv in (0, 1, 2):
+            img = s_mixed(11, 37, bits, cc, layout="planar" if ilv == 0 else "interleaved")
+            cases = [(near, 0, ri) for near in (0, 2) for ri in (1, 0, 4)]
+            if cc == 3 and ilv != 0:
+                cases += [(0, xf, 1) for xf in (1, 2, 3)]
+            for near, xf, ri in cases:
+                got = encode(product, img, bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=ri)
+                want = oracle.encode_image(img, bits, near=near, ilv=ilv, xform=xf, ri=ri)
+                assert payloads(got) == payloads(want), (cc, ilv, bits, near, xf, ri)
+                expected, _ = oracle.decode_image(got)
+                px, _, _ = codec.decode(got, lib=product)
+                assert np.array_equal(px, expected), (cc, ilv, bits, near, xf, ri)
+
+
+CONFIGS = {
+    # BASELINE.json configs[0..3]
+    "cfg1_256_8bit": (lambda: s_smooth(256, 256, 8), 8, 0, 0, 0),
+    "cfg2_4096_8bit": (lambda: s_smooth(4096, 4096, 8), 8, 0, 0, 0),
+    "cfg3_4096_12bit_near2": (lambda: s_smooth(4096, 4096, 12), 12, 2, 0, 0),
+    "cfg4_2048_rgb16_hp1": (lambda: s_smooth(2048, 2048, 16, 3, layout="interleaved"), 16, 0, 2, 1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_baseline_configs_full_size(product, oracle, name):
+    """At BASELINE sizes: the reference decodes our Ri=1 stream to exactly what we decode; lossless round trip;
+    |error| <= NEAR; the first and last lines' bytes equal the oracle's encoding of those rows as W x 1 images."""
+    make, bits, near, ilv, xf = CONFIGS[name]
+    img = make()
+    stream = encode(product, img, bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf)
+    parsed = jlsio.parse(stream)
+    assert parsed.restart_interval == 1
+    px, fi, _ = codec.decode(stream, lib=product)
+    if have_reference_build():
+        want, _, _ = codec.decode(stream, lib=reference_library())
+        assert np.array_equal(px, want)
+    if near == 0:
+        assert np.array_equal(px, img)
+    else:
+        assert int(np.abs(px.astype(np.int64) - img.astype(np.int64)).max()) <= near
+    # line-level byte parity at full width (restart markers delimit the lines)
+    data = stream[parsed.scans[0].data_offset : parsed.scans[0].data_end]
+    lines = []
+    pos = 0
+    while True:
+        i = data.find(b"\xff", pos)
+        if i < 0 or i + 1 >= len(data):
+            lines.append(data[len(b"".join(lines)) + 2 * len(lines) :])
+            break
+        if 0xD0 <= data[i + 1] <= 0xD7:
+            start = len(b"".join(lines)) + 2 * len(lines)
+            lines.append(data[start:i])
+            pos = i + 2
+        else:
+            pos = i + 1
+    assert len(lines) == img.shape[0]
+    for r in (0, 1, img.shape[0] // 2, img.shape[0] - 1):
+        row = img[r : r + 1]
+        want_row = payloads(oracle.encode_image(row, bits, near=near, ilv=ilv, xform=xf))[0]
+        assert lines[r] == want_row, (name, r)
+
+
+def test_idempotent_and_deterministic(product):
+    img = s_mixed(64, 200, 8)
+    a = encode(product, img, 8)
+    b = encode(product, img, 8)
+    assert a == b
+    px, _, _ = codec.decode(a, lib=product)
+    assert encode(product, px, 8) == a
+
+
+def test_strides_and_masking(product, oracle):
+    """Source / destination line padding and unused high bits (reference jpegls_encoder_test.cpp:1421-1755)."""
+    img = s_noise(20, 33, 16)  # 12-bit stream from 16-bit containers: high bits must be ignored
+    stream = encode(product, img, 12)
+    assert payloads(stream) == payloads(oracle.encode_image(img, 12, ri=1))
+    padded = np.zeros((20, 50), np.uint8)
+    src = s_mixed(20, 33, 8)
+    padded[:, :33] = src
+    with codec.JpegLSEncoder(product) as enc:
+        enc.frame_info(33, 20, 8, 1)
+        dst = np.zeros(8192, np.uint8)
+        enc.destination(dst)
+        n = enc.encode(padded, stride=50)
+    assert dst[:n].tobytes() == encode(product, src, 8)
+    with codec.JpegLSDecoder(product) as dec:
+        dec.source(dst[:n].tobytes()).read_header()
+        out = np.full(dec.destination_size(64), 0xAA, np.uint8)
+        dec.decode(out, stride=64)
+    rows = np.full(20 * 64, 0xAA, np.uint8)
+    rows[: len(out)] = out
+    rows = rows.reshape(20, 64)
+    assert np.array_equal(rows[:, :33], src)
+    assert np.all(rows[:-1, 33:] == 0xAA)  # padding untouched
+
+
+def test_destination_too_small(product):
+    img = s_noise(64, 64, 8)
+    with codec.JpegLSEncoder(product) as enc:
+        enc.frame_info(64, 64, 8, 1)
+        dst = np.zeros(600, np.uint8)
+        enc.destination(dst)
+        with pytest.raises(CharlsError) as info:
+            enc.encode(img)
+    assert info.value.errc == 3
+
+
+def test_corrupt_streams_never_hang(product, oracle):
+    """Bit flips, truncation and bad restart markers: an error code or pixels, never a hang (reference fuzz fixtures)."""
+    rng = np.random.default_rng(5)
+    img = s_mixed(40, 120, 8)
+    good = encode(product, img, 8)
+    parsed = jlsio.parse(good)
+    start, end = parsed.scans[0].data_offset, parsed.scans[0].data_end
+    ref = reference_library() if have_reference_build() else None
+    outcomes = set()
+    for trial in range(60):
+        data = bytearray(good)
+        kind = trial % 4
+        if kind == 0:
+            for _ in range(3):
+                data[int(rng.integers(start, end))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            data = data[: int(rng.integers(start, end))]
+        elif kind == 2:
+            i = bytes(data).find(b"\xff\xd3", start)
+            data[i + 1] = 0xD5  # wrong restart marker id
+        else:
+            i = bytes(data).find(b"\xff\xd1", start)
+            del data[i : i + 2]  # missing restart marker
+        data = bytes(data)
+        try:
+            px, _, _ = codec.decode(data, lib=product)
+            ours = 0
+        except CharlsError as e:
+            ours = e.errc
+        outcomes.add(ours)
+        if ref is not None:
+            try:
+                want, _, _ = codec.decode(data, lib=ref)
+                theirs = 0
+            except CharlsError as e:
+                theirs = e.errc
+            if theirs == 0:
+                assert ours == 0 and np.array_equal(px, want), trial
+            else:
+                assert ours != 0, (trial, theirs)
+            if kind in (2, 3):
+                assert ours == theirs == 23, (trial, ours, theirs)  # restart_marker_not_found
+    assert outcomes - {0}
+
+
+def test_instances_on_threads(product, oracle):
+    """Distinct encoder / decoder instances are independent (reference: undocumented but de facto)."""
+    images = [s_mixed(50, 90, 8, seed=i) for i in range(8)]
+    want = [oracle.encode_image(im, 8, ri=1) for im in images]
+    got = [None] * 8
+
+    def work(i):
+        for _ in range(3):
+            s = encode(product, images[i], 8)
+            px, _, _ = codec.decode(s, lib=product)
+            assert np.array_equal(px, images[i])
+        got[i] = s
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for i in range(8):
+        assert payloads(got[i]) == payloads(want[i])
+
+
+def test_batch_interface(product, oracle):
+    """charlsx_batch_*: device-resident frames, same bytes as the single-image ABI, per-frame status."""
+    import torch
+
+    from charls_b200.batch import BatchCodec
+
+    device = torch.device("cuda", 0)
+    for (w, h, bits, cc, near, ilv, xf) in ((96, 40, 8, 1, 0, 0, 0), (50, 21, 12, 1, 2, 0, 0), (33, 17, 16, 3, 0, 2, 1)):
+        n = 5
+        frames_np = [s_mixed(h, w, bits, cc, seed=10 + i, layout="interleaved") for i in range(n)]
+        arr = np.stack(frames_np)
+        t = torch.from_numpy(arr.view(np.int16) if bits > 8 else arr).to(device)
+        bc = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, lib=product)
+        streams = torch.zeros((n, bc.stream_capacity * 2), dtype=torch.uint8, device=device)
+        sizes = bc.encode(t, streams)
+        assert bc.last_kernel_launches() > 0
+        host = streams.cpu().numpy()
+        for i in range(n):
+            single = encode(product, frames_np[i], bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf)
+            assert host[i, : sizes[i]].tobytes() == single, (w, h, bits, i)
+        out = torch.zeros_like(t)
+        bc.decode(streams, sizes, out)
+        got = out.cpu().numpy()
+        got = got.view(np.uint16) if bits > 8 else got
+        for i in range(n):
+            expected, _ = oracle.decode_image(host[i, : sizes[i]].tobytes())
+            assert np.array_equal(got[i], expected), (w, h, bits, i)
+        bc.close()
+    # a stream that is too small is reported per frame, the others are still coded
+    bc = BatchCodec(64, 64, 8, lib=product)
+    t = torch.from_numpy(np.stack([s_noise(64, 64, 8, seed=i) for i in range(3)])).to(device)
+    streams = torch.zeros((3, 512), dtype=torch.uint8, device=device)
+    with pytest.raises(CharlsError) as info:
+        bc.encode(t, streams)
+    assert info.value.errc == 3

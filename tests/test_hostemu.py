@@ -1,0 +1,92 @@
+"""Runs the product's kernel code (charls_b200/csrc/jls_interval.cuh compiled for the host, one interval after the
+other) against the oracle.  This is what keeps the device code honest in the GPU-less container; tests/test_gpu_*.py
+repeat the comparison through the real kernels."""
+import numpy as np
+import pytest
+
+from tests.hostemu_lib import HostEmu
+from tests.support import s_mixed, s_noise, s_smooth
+
+
+@pytest.fixture(scope="module")
+def hostemu():
+    return HostEmu()
+
+
+def check_scan(oracle, he, plane, bits, nc, near, ilv, xf, ri, pc=None):
+    h, w = plane.shape[0], plane.shape[1]
+    sp = oracle.params(w, h, bits, nc, near, ilv, xf, pc, ri)
+    want = oracle.encode_scan(sp, plane)
+    hp = he.params(sp)
+    expected = np.zeros_like(plane)
+    assert oracle.decode_scan(sp, want + b"\xff\xd9", expected) == len(want)
+    for force_general in ((False, True) if he.fast(hp) else (True,)):
+        n, got = he.encode(hp, plane, len(want) + 64, force_general)
+        assert n == len(want) and got == want, ("encode", plane.shape, bits, nc, near, ilv, xf, ri, pc, force_general)
+        out = np.zeros_like(plane)
+        n = he.decode(hp, want + b"\xff\xd9", out, force_general)
+        assert n == len(want) and np.array_equal(out, expected), ("decode", plane.shape, bits, nc, near, ilv, xf, ri, pc, force_general)
+
+
+@pytest.mark.parametrize("bits", [2, 4, 8, 10, 12, 16])
+def test_scalar_lines(oracle, hostemu, bits):
+    for gen in (s_smooth, s_noise, s_mixed):
+        for (h, w) in ((9, 33), (1, 9), (13, 1), (12, 130)):
+            img = gen(h, w, bits)
+            for near in (0, 1, 3):
+                if near > ((1 << bits) - 1) // 2:
+                    continue
+                for ri in (1, 0, 3):
+                    check_scan(oracle, hostemu, img, bits, 1, near, 0, 0, ri)
+
+
+@pytest.mark.parametrize("bits", [5, 8, 16])
+def test_multi_component(oracle, hostemu, bits):
+    for cc in (2, 3, 4):
+        for ilv in (1, 2):
+            for gen in (s_smooth, s_mixed):
+                img = gen(11, 37, bits, cc, layout="interleaved")
+                for near in (0, 2):
+                    for ri in (1, 0, 4):
+                        check_scan(oracle, hostemu, img, bits, cc, near, ilv, 0, ri)
+                if cc == 3 and bits in (8, 16):
+                    for xf in (1, 2, 3):
+                        for ri in (1, 0):
+                            check_scan(oracle, hostemu, img, bits, cc, 0, ilv, xf, ri)
+
+
+def test_presets_masking_and_long_runs(oracle, hostemu):
+    for pc in ((255, 9, 9, 9, 31), (0, 0, 0, 0, 3), (0, 5, 6, 200, 255)):
+        img = s_mixed(17, 65, 8)
+        for ri in (1, 0):
+            check_scan(oracle, hostemu, img, 8, 1, 0, 0, 0, ri, pc)
+            check_scan(oracle, hostemu, img, 8, 1, 2, 0, 0, ri, pc)
+    # unused high bits are masked away (reference copy_to_line_buffer.hpp:106-116)
+    check_scan(oracle, hostemu, s_noise(8, 40, 16), 12, 1, 0, 0, 0, 1)
+    check_scan(oracle, hostemu, s_noise(8, 40, 16, 3, layout="interleaved"), 12, 3, 0, 2, 0, 1)
+    # very long zero runs exercise run_index 31 and lines wider than 65535
+    z = np.zeros((3, 70000), np.uint8)
+    z[1, 69999] = 7
+    z[2, 100] = 9
+    check_scan(oracle, hostemu, z, 8, 1, 0, 0, 0, 1)
+    check_scan(oracle, hostemu, z, 8, 1, 0, 0, 0, 0)
+
+
+def test_golden_vectors(oracle, hostemu, golden):
+    """Kernel code == reference-made streams (restart interval 1 stitched from per-row reference encodings)."""
+    from tests import jlsio
+
+    for v in golden:
+        if v.ilv == 0 and v.image.ndim == 3:
+            continue  # multi-scan: covered per plane by the other tests
+        s = jlsio.parse(v.ri1)
+        sc = s.scans[0]
+        h, w = (v.image.shape[0], v.image.shape[1])
+        sp = oracle.params(w, h, v.bits, sc.component_count, v.near, v.ilv, v.xf, v.pc, 1)
+        hp = hostemu.params(sp)
+        want = v.ri1[sc.data_offset : sc.data_end]
+        n, got = hostemu.encode(hp, v.image, len(want) + 64)
+        assert got == want, v.name
+        out = np.zeros_like(v.image)
+        assert hostemu.decode(hp, want + b"\xff\xd9", out) == len(want), v.name
+        assert np.array_equal(out, v.dec1), v.name
