@@ -41,7 +41,7 @@ REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcharls_ref.so")
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -129,20 +129,45 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the UNMODIFIED reference (oracle/_ref) on the host cores, one frame per thread
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(ref, frames_np, workload, threads):
-    """Encodes and decodes frames_np[i] on `threads` host threads with the reference library. Returns seconds."""
-    from charls_b200 import codec
+def cpu_reference_step(ref, frames_np, workload, threads, buffers=None):
+    """Encodes and decodes frames_np[i] on `threads` host threads with the reference library (objects constructed inside
+    the loop, buffers pre-allocated outside, like the reference's own cli/benchmark.cpp:44-89). Returns seconds."""
+    from charls_b200.capi import FrameInfo
 
     w, h, bits, cc, near, ilv, xf = WORKLOADS[workload]
+    n = len(frames_np)
+    if buffers is None:
+        buffers = {}
+    if "dst" not in buffers:
+        cap = frames_np[0].nbytes + frames_np[0].nbytes // 16 + 2048
+        buffers["dst"] = [np.zeros(cap, np.uint8) for _ in range(n)]
+        buffers["out"] = [np.zeros(frames_np[0].nbytes, np.uint8) for _ in range(n)]
 
     def work(i):
-        s = codec.encode(frames_np[i], bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf, lib=ref)
-        px, _, _ = codec.decode(s, lib=ref)
-        return len(s)
+        src, dst, out = frames_np[i], buffers["dst"][i], buffers["out"][i]
+        e = ref.charls_jpegls_encoder_create()
+        fi = FrameInfo(w, h, bits, cc)
+        ref.check(ref.charls_jpegls_encoder_set_frame_info(e, C.byref(fi)))
+        ref.check(ref.charls_jpegls_encoder_set_near_lossless(e, near))
+        ref.check(ref.charls_jpegls_encoder_set_interleave_mode(e, ilv))
+        ref.check(ref.charls_jpegls_encoder_set_color_transformation(e, xf))
+        ref.check(ref.charls_jpegls_encoder_set_destination_buffer(e, dst.ctypes.data, dst.nbytes))
+        ref.check(ref.charls_jpegls_encoder_encode_from_buffer(e, src.ctypes.data, src.nbytes, 0))
+        written = C.c_size_t()
+        ref.check(ref.charls_jpegls_encoder_get_bytes_written(e, C.byref(written)))
+        ref.charls_jpegls_encoder_destroy(e)
+        d = ref.charls_jpegls_decoder_create()
+        ref.check(ref.charls_jpegls_decoder_set_source_buffer(d, dst.ctypes.data, written.value))
+        ref.check(ref.charls_jpegls_decoder_read_header(d))
+        ref.check(ref.charls_jpegls_decoder_decode_to_buffer(d, out.ctypes.data, out.nbytes, 0))
+        ref.charls_jpegls_decoder_destroy(d)
 
+    workers = [threading.Thread(target=work, args=(i,)) for i in range(n)]
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as pool:
-        list(pool.map(work, range(len(frames_np))))
+    for t in workers:
+        t.start()
+    for t in workers:
+        t.join()
     return time.perf_counter() - t0
 
 
@@ -177,11 +202,12 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     frames = host_frames(args.workload, min(threads, 8))
     frames = [frames[i % len(frames)] for i in range(threads)]  # one frame per thread per step
+    buffers = {}
     for _ in range(args.warmup):
-        cpu_reference_step(ref, frames, args.workload, threads)
+        cpu_reference_step(ref, frames, args.workload, threads, buffers)
     t = 0.0
     for _ in range(args.steps):
-        t += cpu_reference_step(ref, frames, args.workload, threads)
+        t += cpu_reference_step(ref, frames, args.workload, threads, buffers)
     pixels = threads * w * h * args.steps
     value = pixels / t / 1e6
     sample = f"{threads} host threads x 1 frame of {args.workload} per step (reference encode, no restart markers, + decode of its own stream)"
@@ -393,10 +419,11 @@ def run_gpu_arm(args):
         threads = os.cpu_count() or 1
         hf = host_frames(args.workload, min(threads, 4))
         hf = [hf[i % len(hf)] for i in range(threads)]
-        cpu_reference_step(ref, hf, args.workload, threads)  # warm
+        buffers = {}
+        cpu_reference_step(ref, hf, args.workload, threads, buffers)  # warm
         reps, t = 0, 0.0
-        while t < 6.0 and reps < 20:
-            t += cpu_reference_step(ref, hf, args.workload, threads)
+        while t < 8.0 and reps < 20:
+            t += cpu_reference_step(ref, hf, args.workload, threads, buffers)
             reps += 1
         cpu_baseline = {"value": threads * reps * w * h / t / 1e6, "unit": "MPixels/s", "cores": threads, "kind": "reference",
                         "sample": f"{threads} threads x {reps} frames of {args.workload}: unmodified reference encode (no restart markers) + decode"}

@@ -550,7 +550,7 @@ struct BitReader
             zeros += valid;
             cache = 0;
             valid = 0;
-            if (zeros > 96)
+            if (overrun()) // ran off the end of the interval inside a unary code (the reference: invalid_data)
             {
                 bad = true;
                 return 0;

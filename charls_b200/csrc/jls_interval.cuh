@@ -78,10 +78,17 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
 }
 
 // What the reference checks when an interval / the scan ends (src/scan_decoder.hpp:71-89,335-349).
-JLS_HD int32_t interval_end_status(const CodecParams& p, const BitReader& br, bool bad, uint32_t interval)
+JLS_HD int32_t interval_end_status(const CodecParams& p, const BitReader& br, bool bad, uint32_t interval,
+                                   bool closing_marker_found = true)
 {
     if (bad || br.overrun())
         return err_invalid_data;
+    if (!closing_marker_found)
+    {
+        // The data ends without a marker.  The reference's read pointer runs at most one cache (8 bytes) ahead of the
+        // last symbol: at the end of the data it reports need_more_data (left to the finish step), else invalid_data.
+        return br.unread_bytes() > 7 ? err_invalid_data : err_none;
+    }
     if (interval + 1 == p.interval_count)
     {
         // left-over bits must be zero padding and the closing marker must follow directly
@@ -98,9 +105,14 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
     IntervalResult result = {err_none, 0};
     // interval_offset holds 2 entries per interval: [2i] = first byte, [2i+1] = end (first 0xFF of the closing marker)
     const uint64_t begin = job.interval_offset[2 * static_cast<size_t>(interval)];
-    const uint64_t end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
-    if (end == ~0ULL || begin == ~0ULL || begin > end)
-        return result; // marker table incomplete: the finish step reports it
+    uint64_t end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
+    if (begin == ~0ULL)
+        return result; // an earlier restart marker is missing: the finish step reports it
+    const bool closing_marker_found = end != ~0ULL;
+    if (!closing_marker_found)
+        end = job.stream_in_size; // no closing marker: decode what is there (the reference runs dry -> invalid_data)
+    if (begin > end)
+        return result;
 
     FastLineDecoder<NC, LOSSLESS> dec;
     dec.begin(p, contexts, context_stride, job.stream_in + begin, job.stream_in + end);
@@ -144,7 +156,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
             store_pixel<NC>(p, line, x, dec.ra);
         }
     }
-    result.errc = interval_end_status(p, dec.br, dec.bad, interval);
+    result.errc = interval_end_status(p, dec.br, dec.bad, interval, closing_marker_found);
     return result;
 }
 
@@ -231,8 +243,13 @@ JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, con
 {
     IntervalResult result = {err_none, 0};
     const uint64_t begin = job.interval_offset[2 * static_cast<size_t>(interval)];
-    const uint64_t end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
-    if (end == ~0ULL || begin == ~0ULL || begin > end)
+    uint64_t end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
+    if (begin == ~0ULL)
+        return result;
+    const bool closing_marker_found = end != ~0ULL;
+    if (!closing_marker_found)
+        end = job.stream_in_size;
+    if (begin > end)
         return result;
 
     const int32_t width = p.width, ps = width + 2, nc = p.components;
@@ -289,7 +306,7 @@ JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, con
             }
         }
     }
-    result.errc = interval_end_status(p, br, state.bad, interval);
+    result.errc = interval_end_status(p, br, state.bad, interval, closing_marker_found);
     return result;
 }
 

@@ -339,13 +339,8 @@ __global__ void k_decode_finish(const __grid_constant__ CodecParams p, const Sca
     const ScanJob& job = jobs[j];
     const uint32_t found = marker_totals[j];
     const uint8_t* codes = marker_codes + static_cast<size_t>(j) * p.interval_count;
-    for (uint32_t i = 0; i + 1 < p.interval_count; ++i)
+    for (uint32_t i = 0; i + 1 < p.interval_count && i < found; ++i)
     {
-        if (i >= found)
-        {
-            report_error(job, i, err_need_more_data);
-            break;
-        }
         if (codes[i] != 0xD0U + (i & 7U)) // reference src/scan_decoder.hpp:335-349
         {
             report_error(job, i, err_restart_marker_not_found);
@@ -354,7 +349,10 @@ __global__ void k_decode_finish(const __grid_constant__ CodecParams p, const Sca
     }
     if (found < p.interval_count)
     {
-        report_error(job, found, err_need_more_data);
+        // The data ends inside interval `found`.  The reference either ran out of bits while decoding it
+        // (invalid_data, already reported by the decode kernel) or finds nothing where the marker should be.
+        if ((*job.status >> 8) != found)
+            report_error(job, found, err_need_more_data);
         job.result[0] = job.stream_in_size;
     }
     else

@@ -1156,6 +1156,8 @@ int64_t jls_oracle_decode_scan(const jls_scan_params* p, const uint8_t* source, 
     {
         /* src/scan_decoder.hpp:71-89: must sit on a marker, left-over (padding) bits must be zero */
         br_finish_interval(s);
+        if (s->in_pos < s->in_end && s->in[s->in_pos] != 0xFF)
+            br_fill(s); /* the reference's read pointer runs up to one cache ahead of the last symbol */
         if (s->in_pos >= s->in_end)
             s->error = JLS_ORACLE_ERR_NEED_MORE_DATA;
         else if (s->in[s->in_pos] != 0xFF || s->rcache != 0)

@@ -149,20 +149,15 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
             report(i, r.errc);
     }
     // k_decode_finish
-    for (uint32_t i = 0; i + 1 < p.interval_count; ++i)
+    for (uint32_t i = 0; i + 1 < p.interval_count && i < found; ++i)
     {
-        if (i >= found)
-        {
-            report(i, err_need_more_data);
-            break;
-        }
         if (codes[i] != 0xD0U + (i & 7U))
         {
             report(i, err_restart_marker_not_found);
             break;
         }
     }
-    if (found < p.interval_count)
+    if (found < p.interval_count && (first_error >> 8) != found)
         report(found, err_need_more_data);
     if (first_error != ~0ULL)
         return -static_cast<int64_t>(first_error & 0xFF);
