@@ -4,10 +4,10 @@
 // the unit tests (tests/hostemu); the product only ever calls it from the kernels in jls_kernels.cu.
 //
 // Two codecs are built from one set of primitives:
-//   * FastLineEncoder / FastLineDecoder -- restart interval = 1 line.  The previous line is all zeros at every
-//     restart (reference src/scan_decoder_impl.hpp:122-127), so Rb = Rc = Rd = 0, the gradient vector collapses to
-//     (0, 0, -Ra) and only contexts 0..4 exist: the whole adaptive state of a line lives in registers plus 80 bytes
-//     of shared memory per thread.  One thread codes one line; a warp codes 32 lines.
+//   * FastLineEncoder / FastLineDecoder (jls_fast.cuh) -- restart interval = 1 line.  The previous line is all zeros
+//     at every restart (reference src/scan_decoder_impl.hpp:122-127), so Rb = Rc = Rd = 0, the gradient vector
+//     collapses to (0, 0, -Ra) and only contexts 0..4 exist: the whole adaptive state of a line lives in registers plus
+//     80 bytes of shared memory per thread.  One thread codes one line; a warp codes 32 lines.
 //   * GeneralIntervalEncoder / GeneralIntervalDecoder -- any restart interval (including none): full 2-D LOCO-I with
 //     365 contexts, one thread per restart interval.  Needed to decode every conformant stream and to write
 //     streams that are byte-identical to the reference's (restart interval 0).
@@ -374,28 +374,24 @@ struct BitWriter
     JLS_HD void put_golomb(int32_t k, int32_t mapped, int32_t limit, int32_t qbpp)
     {
         const int32_t high = mapped >> k;
-        if (high < limit - qbpp - 1)
+        const int32_t escape = limit - qbpp - 1;
+        if (high < escape && high + 1 + k <= 32)
         {
-            if (high + 1 + k <= 32)
-            {
-                put((1U << k) | (static_cast<uint32_t>(mapped) & ((1U << k) - 1U)), high + 1 + k);
-            }
-            else
-            {
-                put(0, high - 16); // high <= 46
-                put(1, 17);
-                put(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
-            }
+            put((1U << k) | (static_cast<uint32_t>(mapped) & ((1U << k) - 1U)), high + 1 + k);
             return;
         }
-        int32_t zeros = limit - qbpp - 1;
+        // long code word (more than 32 bits) or escape code: unary part in at most two pieces, then the binary part
+        int32_t zeros = high < escape ? high : escape;
         if (zeros > 31)
         {
             put(0, 31);
             zeros -= 31;
         }
         put(1, zeros + 1);
-        put(static_cast<uint32_t>(mapped - 1) & ((1U << qbpp) - 1U), qbpp);
+        if (high < escape)
+            put(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
+        else
+            put(static_cast<uint32_t>(mapped - 1) & ((1U << qbpp) - 1U), qbpp);
     }
 
     // End of a restart interval / scan (reference src/scan_encoder.hpp:103-115): pad with zero bits to a byte; a final
@@ -727,226 +723,6 @@ JLS_HD void color_inverse(int32_t transform, int32_t type_mask, int32_t& c0, int
         c2 = (v2 + g - bias) & type_mask;
     }
 }
-
-// ---------------------------------------------------------------------------------------------------------------------
-// FAST PATH: restart interval = 1 line.  Per-thread state for one line.
-//
-// `contexts` points at this thread's five regular contexts (index = |Q(-Ra)| in 0..4); consecutive contexts are
-// `context_stride` RegularContext apart (32 on the GPU: [context][lane] in shared memory, so a warp-wide 16-byte access
-// is conflict free; 1 on the host).  The context in use is cached in registers and only written back when the next
-// sample selects a different one.
-// ---------------------------------------------------------------------------------------------------------------------
-template<int NC>
-struct FastLineState
-{
-    RegularContext* contexts;
-    int32_t context_stride;
-    RegularContext cached;
-    int32_t cached_index;
-    RunContext run_context; // scalar lines only ever use RItype 1, multi-component pixels only RItype 0
-    int32_t run_index;
-    int32_t ra[NC];
-    bool bad;
-
-    JLS_HD void begin_interval(const CodecParams& p, RegularContext* ctx, int32_t stride)
-    {
-        contexts = ctx;
-        context_stride = stride;
-        const RegularContext initial = {p.a_init, 0, 0, 1};
-        for (int32_t q = 0; q < 5; ++q)
-            contexts[q * stride] = initial;
-        cached = initial;
-        cached_index = 4;
-        run_context.a = p.a_init;
-        run_context.n = 1;
-        run_context.nn = 0;
-        bad = false;
-        begin_line();
-    }
-
-    // every line of an interval starts from an all-zero neighbourhood and run index 0 (one line per component per interval)
-    JLS_HD void begin_line()
-    {
-        run_index = 0;
-        for (int32_t c = 0; c < NC; ++c)
-            ra[c] = 0;
-    }
-
-    JLS_HD RegularContext& select_context(int32_t index)
-    {
-        if (index != cached_index)
-        {
-            contexts[cached_index * context_stride] = cached;
-            cached = contexts[index * context_stride];
-            cached_index = index;
-        }
-        return cached;
-    }
-
-    // |Q(-Ra)|: di = -Ra <= -T3 -> 4, <= -T2 -> 3, <= -T1 -> 2, < -NEAR -> 1, else 0 (jpegls_algorithm.hpp:173-194)
-    static JLS_HD int32_t context_index(const CodecParams& p, int32_t ra_value)
-    {
-        return (ra_value >= p.t3) + (ra_value >= p.t2) + (ra_value >= p.t1) + (ra_value > p.near);
-    }
-
-    JLS_HD bool in_run_mode(const CodecParams& p) const
-    {
-        bool all_zero = true;
-        for (int32_t c = 0; c < NC; ++c)
-            all_zero = all_zero && ra[c] <= p.near;
-        return all_zero;
-    }
-};
-
-template<int NC, bool LOSSLESS>
-struct FastLineEncoder : FastLineState<NC>
-{
-    BitWriter bw;
-    int32_t run_count;
-
-    JLS_HD void begin(const CodecParams& p, RegularContext* ctx, int32_t stride, uint8_t* slot, size_t capacity)
-    {
-        this->begin_interval(p, ctx, stride);
-        bw.init(slot, capacity);
-        run_count = 0;
-    }
-
-    // Codes one pixel (NC samples, already masked / colour transformed). `last` = last pixel of the line.
-    JLS_HD void pixel(const CodecParams& p, const int32_t (&x)[NC], bool last)
-    {
-        if (this->in_run_mode(p))
-        {
-            bool same = true;
-            for (int32_t c = 0; c < NC; ++c)
-                same = same && iabs(x[c] - this->ra[c]) <= p.near;
-            if (same)
-            {
-                // run continues; reconstructed value is Ra (scan_encoder_impl.hpp:258-265)
-                ++run_count;
-                if (last)
-                {
-                    encode_run_length(bw, this->run_index, run_count, true);
-                    run_count = 0;
-                }
-                return;
-            }
-            encode_run_length(bw, this->run_index, run_count, false);
-            run_count = 0;
-            for (int32_t c = 0; c < NC; ++c)
-            {
-                if (NC == 1)
-                {
-                    // Rb = 0 and Ra <= NEAR: |Ra - Rb| <= NEAR always -> RItype 1 (scan_encoder_core.hpp:118-125)
-                    const int32_t e = compute_error_value<LOSSLESS>(p, x[c] - this->ra[c]);
-                    encode_run_interruption_error(p, bw, this->run_context, 1, e, this->run_index);
-                    this->ra[c] = LOSSLESS ? x[c] : reconstruct<false>(p, this->ra[c], e);
-                }
-                else
-                {
-                    // per component, RItype 0, prediction Rb = 0 (scan_encoder_core.hpp:133-138)
-                    const int32_t s = sign_of(-this->ra[c]);
-                    const int32_t e = compute_error_value<LOSSLESS>(p, s * x[c]);
-                    encode_run_interruption_error(p, bw, this->run_context, 0, e, this->run_index);
-                    this->ra[c] = LOSSLESS ? x[c] : reconstruct<false>(p, 0, e * s);
-                }
-            }
-            if (this->run_index > 0)
-                --this->run_index;
-            return;
-        }
-        for (int32_t c = 0; c < NC; ++c)
-        {
-            const int32_t q = FastLineState<NC>::context_index(p, this->ra[c]);
-            RegularContext& ctx = this->select_context(q);
-            // prediction = Ra (MED of (Ra, 0, 0)); sign is negative for every non-zero context (Q3 < 0)
-            this->ra[c] = encode_regular_sample<LOSSLESS>(p, bw, ctx, q != 0 ? -1 : 0, x[c], this->ra[c], this->bad);
-        }
-    }
-
-    JLS_HD uint32_t finish() { return bw.finish(); }
-};
-
-template<int NC, bool LOSSLESS>
-struct FastLineDecoder : FastLineState<NC>
-{
-    BitReader br;
-    int32_t run_left;    // pixels of the current run still to be output
-    bool need_interrupt; // a run-interruption pixel follows the current run
-
-    JLS_HD void begin(const CodecParams& p, RegularContext* ctx, int32_t stride, const uint8_t* begin_, const uint8_t* end_)
-    {
-        this->begin_interval(p, ctx, stride);
-        br.init(begin_, end_);
-        run_left = 0;
-        need_interrupt = false;
-    }
-
-    JLS_HD void begin_line()
-    {
-        FastLineState<NC>::begin_line();
-        run_left = 0;
-        need_interrupt = false;
-    }
-
-    JLS_HD void decode_interruption(const CodecParams& p)
-    {
-        for (int32_t c = 0; c < NC; ++c)
-        {
-            if (NC == 1)
-            {
-                const int32_t e = decode_run_interruption_error(p, br, this->run_context, 1, this->run_index, this->bad);
-                this->ra[c] = reconstruct<LOSSLESS>(p, this->ra[c], e);
-            }
-            else
-            {
-                const int32_t s = sign_of(-this->ra[c]);
-                const int32_t e = decode_run_interruption_error(p, br, this->run_context, 0, this->run_index, this->bad);
-                this->ra[c] = reconstruct<LOSSLESS>(p, 0, e * s);
-            }
-        }
-        if (this->run_index > 0)
-            --this->run_index;
-        need_interrupt = false;
-    }
-
-    // Decodes one pixel into this->ra (which is also the decoded pixel). `remaining` = pixels left in the line incl. this one.
-    JLS_HD void pixel(const CodecParams& p, int32_t remaining)
-    {
-        if (run_left > 0)
-        {
-            --run_left;
-            return;
-        }
-        if (need_interrupt)
-        {
-            decode_interruption(p);
-            return;
-        }
-        if (this->in_run_mode(p))
-        {
-            const int32_t length = decode_run_length(br, this->run_index, remaining);
-            if (length < 0)
-            {
-                this->bad = true; // reference scan_decoder_impl.hpp:328-329
-                return;
-            }
-            need_interrupt = length != remaining;
-            if (length > 0)
-            {
-                run_left = length - 1;
-                return;
-            }
-            decode_interruption(p);
-            return;
-        }
-        for (int32_t c = 0; c < NC; ++c)
-        {
-            const int32_t q = FastLineState<NC>::context_index(p, this->ra[c]);
-            RegularContext& ctx = this->select_context(q);
-            this->ra[c] = decode_regular_sample<LOSSLESS>(p, br, ctx, q != 0 ? -1 : 0, this->ra[c], this->bad);
-        }
-    }
-};
 
 // ---------------------------------------------------------------------------------------------------------------------
 // GENERAL PATH: any restart interval, full 2-D neighbourhood, 365 + 2 contexts in (thread-)local memory.

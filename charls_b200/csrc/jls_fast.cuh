@@ -1,0 +1,693 @@
+// jls_fast.cuh -- the restart-interval-1 line codec, written for instruction count.
+//
+// With one restart interval per line the previous line is all zeros at every line start (reference
+// src/scan_decoder_impl.hpp:122-127), so Rb = Rc = Rd = 0: the gradient vector is (0, 0, -Ra), the MED prediction is Ra,
+// and only contexts 0..4 (index |Q(-Ra)|) exist.  One thread codes one line, a warp 32 lines in
+// lock step, one pixel per loop iteration.  The kernels are bound by instruction issue (ncu: profiles/), so this file
+// is about executing few instructions per pixel AND about keeping the rare paths rare for the whole warp:
+//   * coding parameters live in registers (HotParams), not in the constant bank;
+//   * the bit writer / reader move 32 bits at a time on a straight-line path; byte-wise code runs only around 0xFF
+//     bytes and at the ends of a line;
+//   * the context in use is cached in registers; the five contexts of a thread sit in shared memory as
+//     [context][thread] (conflict-free 16-byte accesses) and are touched only when the context changes;
+//   * conditions that cannot occur for valid input are not checked in the encoder (the decoder checks everything the
+//     reference checks, it sees untrusted data).
+// Everything is __host__ __device__: tests/hostemu runs this very code on the CPU against the oracle.
+#pragma once
+
+#include "jls_codec.cuh"
+
+#if defined(__GNUC__) || defined(__CUDACC__)
+#define JLS_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define JLS_LIKELY(x) __builtin_expect(!!(x), 1)
+#else
+#define JLS_UNLIKELY(x) (x)
+#define JLS_LIKELY(x) (x)
+#endif
+
+namespace jls {
+
+// The coding parameters a line needs, held in registers.
+struct HotParams
+{
+    int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init;
+    uint32_t dq_magic;
+};
+
+JLS_HD HotParams make_hot_params(const CodecParams& p)
+{
+    HotParams h;
+    h.t1 = p.t1;
+    h.t2 = p.t2;
+    h.t3 = p.t3;
+    h.near = p.near;
+    h.maxval = p.maxval;
+    h.limit = p.limit;
+    h.qbpp = p.qbpp;
+    h.reset = p.reset;
+    h.bits = p.bits_per_sample;
+    h.escape = p.limit - p.qbpp - 1;
+    h.dq = p.dq;
+    h.range = p.range;
+    h.range_dq = p.range_dq;
+    h.a_init = p.a_init;
+    h.dq_magic = p.dq_magic;
+#if defined(__CUDA_ARCH__)
+    // keep the hot ones in registers instead of re-reading the constant bank in every iteration
+    asm volatile("" : "+r"(h.t1), "+r"(h.t2), "+r"(h.t3), "+r"(h.reset), "+r"(h.escape), "+r"(h.maxval), "+r"(h.bits));
+#endif
+    return h;
+}
+
+template<bool LOSSLESS>
+JLS_HD int32_t fast_error_value(const HotParams& h, int32_t e)
+{
+    if (LOSSLESS)
+    {
+        const int32_t shift = 32 - h.bits;
+        return static_cast<int32_t>(static_cast<uint32_t>(e) << shift) >> shift;
+    }
+    int32_t q = static_cast<int32_t>(mulhi32(static_cast<uint32_t>(iabs(e) + h.near), h.dq_magic));
+    q = e > 0 ? q : -q;
+    if (q < 0)
+        q += h.range;
+    if (q >= (h.range + 1) / 2)
+        q -= h.range;
+    return q;
+}
+
+JLS_HD int32_t fast_clamp(const HotParams& h, int32_t v) // == correct_prediction: v in [0, maxval] or the nearer bound
+{
+    return imin(imax(v, 0), h.maxval);
+}
+
+template<bool LOSSLESS>
+JLS_HD int32_t fast_reconstruct(const HotParams& h, int32_t predicted, int32_t error_value)
+{
+    if (LOSSLESS)
+        return (predicted + error_value) & h.maxval;
+    int32_t v = predicted + error_value * h.dq;
+    if (v < -h.near)
+        v += h.range_dq;
+    else if (v > h.maxval + h.near)
+        v -= h.range_dq;
+    return fast_clamp(h, v);
+}
+
+// T.87 A.12 / A.13 without the reference's sanity check (src/regular_mode_context.hpp:45-94); branch-light.
+template<bool LOSSLESS>
+JLS_HD void fast_update_context(const HotParams& h, RegularContext& c, int32_t e)
+{
+    c.a += iabs(e);
+    c.b += LOSSLESS ? e : e * h.dq;
+    if (JLS_UNLIKELY(c.n == h.reset))
+    {
+        c.a >>= 1;
+        c.b >>= 1;
+        c.n >>= 1;
+    }
+    ++c.n;
+    const int32_t t = c.b + c.n;
+    const bool low = t <= 0;
+    const bool high = c.b > 0;
+    const int32_t b_low = imax(t, 1 - c.n);
+    const int32_t b_high = imin(c.b - c.n, 0);
+    const int32_t c_low = imax(c.c - 1, -128);
+    const int32_t c_high = imin(c.c + 1, 127);
+    c.b = low ? b_low : (high ? b_high : c.b);
+    c.c = low ? c_low : (high ? c_high : c.c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Bit writer for a slot that is large enough by construction (worst_case_interval_bytes): no capacity checks.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FastWriter
+{
+    uint64_t acc;        // pending bits in the low `nbits` bits
+    int32_t nbits;       // < 32 between calls
+    uint32_t pend;       // pending output bytes in the low pend_shift / 8 bytes
+    uint32_t pend_shift; // 8 * (number of pending bytes), 0..24
+    uint32_t prev_ff;    // last emitted byte was 0xFF
+    uint32_t* wp;
+    uint32_t* base;
+
+    JLS_HD void init(uint8_t* destination)
+    {
+        acc = 0;
+        nbits = 0;
+        pend = 0;
+        pend_shift = 0;
+        prev_ff = 0;
+        base = reinterpret_cast<uint32_t*>(destination);
+        wp = base;
+    }
+
+    JLS_HD void emit_byte(uint32_t b)
+    {
+        pend = (pend << 8) | b;
+        pend_shift += 8;
+        if (pend_shift == 32)
+        {
+            *wp++ = bswap32(pend);
+            pend_shift = 0;
+        }
+    }
+
+    JLS_HD void emit_one_stuffed_byte()
+    {
+        const int32_t take = prev_ff ? 7 : 8;
+        const uint32_t b = static_cast<uint32_t>(acc >> (nbits - take)) & (0xFFU >> (8 - take));
+        nbits -= take;
+        emit_byte(b);
+        prev_ff = (b == 0xFFU) ? 1U : 0U;
+    }
+
+    // value < 2^count, count in [0, 32]; nbits < 32 on entry and on exit
+    JLS_HD void put(uint32_t value, int32_t count)
+    {
+        acc = (acc << count) | value;
+        nbits += count;
+        if (nbits >= 32)
+        {
+            const uint32_t w = static_cast<uint32_t>(acc >> (nbits - 32));
+            if (JLS_LIKELY((prev_ff | has_ff_byte(w)) == 0))
+            {
+                *wp++ = bswap32(funnel_r(w, pend, pend_shift));
+                pend = w;
+                nbits -= 32;
+            }
+            else
+            {
+                do
+                {
+                    emit_one_stuffed_byte();
+                } while (nbits >= 32);
+            }
+        }
+    }
+
+    // limited-length Golomb code (T.87 A.5.3; reference src/scan_encoder_core.hpp:69-103)
+    JLS_HD void put_golomb(const HotParams& h, int32_t k, int32_t mapped, int32_t escape)
+    {
+        const int32_t high = mapped >> k;
+        const int32_t length = high + 1 + k;
+        if (JLS_LIKELY(high < escape && length <= 32))
+        {
+            put((1U << k) | (static_cast<uint32_t>(mapped) & ((1U << k) - 1U)), length);
+            return;
+        }
+        // long code word (more than 32 bits) or escape code: unary part in at most two pieces, then the binary part
+        int32_t zeros = high < escape ? high : escape;
+        if (zeros > 31)
+        {
+            put(0, 31);
+            zeros -= 31;
+        }
+        put(1, zeros + 1);
+        if (high < escape)
+            put(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
+        else
+            put(static_cast<uint32_t>(mapped - 1) & ((1U << h.qbpp) - 1U), h.qbpp);
+    }
+
+    // reference src/scan_encoder.hpp:103-115: zero-pad to a byte; a final 0xFF is followed by a zero byte
+    JLS_HD uint32_t finish()
+    {
+        for (;;)
+        {
+            const int32_t take = prev_ff ? 7 : 8;
+            if (nbits < take)
+                break;
+            emit_one_stuffed_byte();
+        }
+        if (nbits > 0)
+        {
+            const int32_t take = prev_ff ? 7 : 8;
+            const uint32_t b = (static_cast<uint32_t>(acc) & ((1U << nbits) - 1U)) << (take - nbits);
+            nbits = 0;
+            emit_byte(b);
+            prev_ff = 0;
+        }
+        if (prev_ff)
+        {
+            emit_byte(0);
+            prev_ff = 0;
+        }
+        const uint32_t bytes = static_cast<uint32_t>(wp - base) * 4U + pend_shift / 8U;
+        if (pend_shift != 0)
+            *wp++ = bswap32(pend << (32 - pend_shift));
+        return bytes;
+    }
+};
+
+// reference src/scan_encoder.hpp:53-73
+JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t run_length, bool end_of_line)
+{
+    while (run_length >= (1 << run_order(run_index)))
+    {
+        bw.put(1, 1);
+        run_length -= 1 << run_order(run_index);
+        if (run_index < 31)
+            ++run_index;
+    }
+    if (end_of_line)
+    {
+        if (run_length != 0)
+            bw.put(1, 1);
+    }
+    else
+    {
+        bw.put(static_cast<uint32_t>(run_length), run_order(run_index) + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Bit reader over [begin, end) of one interval; bytes past `end` read as zero and are accounted for.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FastReader
+{
+    uint64_t cache;       // left aligned
+    int32_t valid;        // valid bits in cache
+    int32_t virtual_bits; // appended bits that lie beyond the end of the interval
+    int32_t remaining;    // real bytes not yet moved into the cache (may go negative)
+    int32_t guard;        // > 0 while the word after `cur` still holds bytes of the interval
+    uint32_t prev_ff;
+    const uint32_t* wptr; // aligned word that holds the next byte to fetch
+    uint32_t cur;         // *wptr
+    uint32_t shift;       // 8 * (offset of the next byte inside *wptr)
+
+    JLS_HD void init(const uint8_t* begin, const uint8_t* end)
+    {
+        cache = 0;
+        valid = 0;
+        virtual_bits = 0;
+        prev_ff = 0;
+        remaining = static_cast<int32_t>(end - begin);
+        const uintptr_t address = reinterpret_cast<uintptr_t>(begin);
+        wptr = reinterpret_cast<const uint32_t*>(address & ~static_cast<uintptr_t>(3));
+        const int32_t offset = static_cast<int32_t>(address & 3U);
+        shift = static_cast<uint32_t>(offset) * 8U;
+        guard = remaining - (4 - offset);
+        cur = remaining > 0 ? *wptr : 0U;
+        refill();
+    }
+
+    JLS_HD void append_byte(uint32_t b, bool is_virtual)
+    {
+        const int32_t take = prev_ff ? 7 : 8;
+        cache |= static_cast<uint64_t>(b & (0xFFU >> (8 - take))) << (64 - take - valid);
+        valid += take;
+        if (is_virtual)
+            virtual_bits += take;
+        prev_ff = (b == 0xFFU) ? 1U : 0U;
+    }
+
+    JLS_HD void refill_once() // valid <= 32 on entry
+    {
+        const uint32_t next = guard > 0 ? wptr[1] : 0U;
+        const uint32_t w = bswap32(funnel_r(cur, next, shift)); // the next four bytes, first one on top
+        cur = next;
+        ++wptr;
+        guard -= 4;
+        if (JLS_LIKELY(remaining >= 4 && (prev_ff | has_ff_byte(w)) == 0))
+        {
+            cache |= static_cast<uint64_t>(w) << (32 - valid);
+            valid += 32;
+        }
+        else
+        {
+            for (int32_t i = 0; i < 4; ++i)
+            {
+                const bool is_virtual = i >= remaining;
+                append_byte(is_virtual ? 0U : (w >> (24 - 8 * i)) & 0xFFU, is_virtual);
+            }
+        }
+        remaining -= 4;
+    }
+
+    JLS_HD void refill() // afterwards valid > 32
+    {
+        while (valid <= 32)
+            refill_once();
+    }
+
+    JLS_HD uint32_t read(int32_t count) // count in [1, 31]
+    {
+        if (JLS_UNLIKELY(valid < count))
+            refill();
+        const uint32_t v = static_cast<uint32_t>(cache >> (64 - count));
+        cache <<= count;
+        valid -= count;
+        return v;
+    }
+
+    JLS_HD bool overrun() const { return valid < virtual_bits; }
+
+    // whole unread bytes left in the interval after the last decoded symbol
+    JLS_HD int32_t unread_bytes() const
+    {
+        const int32_t real_valid_bits = valid - virtual_bits;
+        return (real_valid_bits > 0 ? real_valid_bits / 8 : 0) + (remaining > 0 ? remaining : 0);
+    }
+
+    // limited-length Golomb code (reference src/scan_decoder.hpp:113-125,203-217); `bad` on a malformed code
+    JLS_HD int32_t get_golomb(const HotParams& h, int32_t k, int32_t escape, bool& bad)
+    {
+        if (valid <= 32)
+            refill();
+        const uint32_t top = static_cast<uint32_t>(cache >> 32);
+        const int32_t z = clz32(top);
+        const int32_t length = z + 1 + k;
+        if (JLS_LIKELY(z < escape && length <= 32))
+        {
+            // the whole code word sits in the top 32 bits (valid > 32)
+            const uint32_t remainder = ((top << z) << 1) >> 1 >> (31 - k);
+            cache <<= length;
+            valid -= length;
+            return (z << k) + static_cast<int32_t>(remainder);
+        }
+        int32_t zeros = 0;
+        for (;;)
+        {
+            if (valid <= 32)
+                refill();
+            const int32_t n = clz64(cache);
+            if (n < valid)
+            {
+                zeros += n;
+                cache = (cache << n) << 1;
+                valid -= n + 1;
+                break;
+            }
+            zeros += valid;
+            cache = 0;
+            valid = 0;
+            if (overrun()) // ran off the end of the interval inside a unary code (the reference: invalid_data)
+            {
+                bad = true;
+                return 0;
+            }
+        }
+        if (zeros < escape)
+            return k == 0 ? zeros : (zeros << k) + static_cast<int32_t>(read(k));
+        return static_cast<int32_t>(read(h.qbpp)) + 1;
+    }
+};
+
+// reference src/scan_decoder_impl.hpp:305-337; -1 when the run passes the end of the line
+JLS_HD int32_t fast_decode_run_length(FastReader& br, int32_t& run_index, int32_t pixel_count)
+{
+    int32_t index = 0;
+    while (br.read(1) != 0)
+    {
+        const int32_t block = 1 << run_order(run_index);
+        const int32_t count = imin(block, pixel_count - index);
+        index += count;
+        if (count == block && run_index < 31)
+            ++run_index;
+        if (index == pixel_count)
+            break;
+    }
+    if (index != pixel_count)
+    {
+        const int32_t j = run_order(run_index);
+        if (j > 0)
+            index += static_cast<int32_t>(br.read(j));
+    }
+    return index > pixel_count ? -1 : index;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-line state shared by encoder and decoder
+// ---------------------------------------------------------------------------------------------------------------------
+template<int NC>
+struct FastLineState
+{
+    RegularContext* contexts; // this thread's context q lives at contexts[q * context_stride]
+    int32_t context_stride;
+    RegularContext cached;
+    int32_t cached_index;
+    RunContext run_context; // scalar lines only ever use RItype 1, multi-component pixels only RItype 0
+    int32_t run_index;
+    int32_t ra[NC];
+
+    JLS_HD void begin_interval(const HotParams& h, RegularContext* ctx, int32_t stride)
+    {
+        contexts = ctx;
+        context_stride = stride;
+        const RegularContext initial = {h.a_init, 0, 0, 1};
+        for (int32_t q = 0; q < 5; ++q)
+            contexts[q * stride] = initial;
+        cached = initial;
+        cached_index = 4;
+        run_context.a = h.a_init;
+        run_context.n = 1;
+        run_context.nn = 0;
+        begin_line();
+    }
+
+    // every line of an interval starts from an all-zero neighbourhood and run index 0
+    JLS_HD void begin_line()
+    {
+        run_index = 0;
+        for (int32_t c = 0; c < NC; ++c)
+            ra[c] = 0;
+    }
+
+    JLS_HD void select_context(int32_t index)
+    {
+        if (index != cached_index)
+        {
+            contexts[cached_index * context_stride] = cached;
+            cached = contexts[index * context_stride];
+            cached_index = index;
+        }
+    }
+
+    // |Q(-Ra)|: di = -Ra <= -T3 -> 4, <= -T2 -> 3, <= -T1 -> 2, < -NEAR -> 1, else 0 (jpegls_algorithm.hpp:173-194)
+    static JLS_HD int32_t context_index(const HotParams& h, int32_t ra_value)
+    {
+        return (ra_value >= h.t3) + (ra_value >= h.t2) + (ra_value >= h.t1) + (ra_value > h.near);
+    }
+
+    JLS_HD bool in_run_mode(const HotParams& h) const
+    {
+        if (NC == 1)
+            return ra[0] <= h.near;
+        int32_t m = ra[0];
+        for (int32_t c = 1; c < NC; ++c)
+            m = imax(m, ra[c]);
+        return m <= h.near;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Encoder
+// ---------------------------------------------------------------------------------------------------------------------
+template<int NC, bool LOSSLESS>
+struct FastLineEncoder : FastLineState<NC>
+{
+    FastWriter bw;
+    int32_t run_count;
+
+    JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, uint8_t* slot)
+    {
+        this->begin_interval(h, ctx, stride);
+        bw.init(slot);
+        run_count = 0;
+    }
+
+    JLS_HD void begin_line()
+    {
+        FastLineState<NC>::begin_line();
+        run_count = 0;
+    }
+
+    // regular mode for one sample (reference src/scan_encoder_core.hpp:40-55); prediction = Ra, sign < 0 unless q == 0
+    JLS_HD int32_t regular(const HotParams& h, int32_t x, int32_t ra_value)
+    {
+        const int32_t q = FastLineState<NC>::context_index(h, ra_value);
+        this->select_context(q);
+        RegularContext& c = this->cached;
+        const int32_t k = golomb_parameter(c.a, c.n);
+        const bool negative = NC == 1 || q != 0; // a scalar line reaches regular mode only with q != 0
+        const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
+        const int32_t e = fast_error_value<LOSSLESS>(h, negative ? pv - x : x - pv);
+        const int32_t correction = (LOSSLESS ? k : (k | h.near)) == 0 ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
+        bw.put_golomb(h, k, map_error_value(correction ^ e), h.limit - h.qbpp - 1);
+        fast_update_context<LOSSLESS>(h, c, e);
+        return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
+    }
+
+    // run interruption (reference src/scan_encoder_core.hpp:105-138)
+    JLS_HD void interruption_error(const HotParams& h, int32_t ri_type, int32_t e)
+    {
+        RunContext& c = this->run_context;
+        const int32_t k = run_golomb_parameter(c, ri_type);
+        const int32_t map = run_compute_map(c, e, k);
+        const int32_t e_mapped = 2 * iabs(e) - ri_type - map;
+        bw.put_golomb(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
+        update_run_context(c, e, e_mapped, ri_type, h.reset);
+    }
+
+    // Codes one pixel (NC samples, already masked / colour transformed).
+    JLS_HD void pixel(const HotParams& h, const int32_t (&x)[NC])
+    {
+        if (JLS_UNLIKELY(this->in_run_mode(h)))
+        {
+            bool same = true;
+            for (int32_t c = 0; c < NC; ++c)
+                same = same && iabs(x[c] - this->ra[c]) <= h.near;
+            if (same)
+            {
+                ++run_count; // reconstructed value is Ra (scan_encoder_impl.hpp:258-265)
+                return;
+            }
+            fast_encode_run_length(bw, this->run_index, run_count, false);
+            run_count = 0;
+            for (int32_t c = 0; c < NC; ++c)
+            {
+                if (NC == 1)
+                {
+                    // Rb = 0 and Ra <= NEAR: |Ra - Rb| <= NEAR always -> RItype 1 (scan_encoder_core.hpp:118-125)
+                    const int32_t e = fast_error_value<LOSSLESS>(h, x[c] - this->ra[c]);
+                    interruption_error(h, 1, e);
+                    this->ra[c] = LOSSLESS ? x[c] : fast_reconstruct<false>(h, this->ra[c], e);
+                }
+                else
+                {
+                    // per component, RItype 0, prediction Rb = 0 (scan_encoder_core.hpp:133-138)
+                    const int32_t s = sign_of(-this->ra[c]);
+                    const int32_t e = fast_error_value<LOSSLESS>(h, s * x[c]);
+                    interruption_error(h, 0, e);
+                    this->ra[c] = LOSSLESS ? x[c] : fast_reconstruct<false>(h, 0, e * s);
+                }
+            }
+            if (this->run_index > 0)
+                --this->run_index;
+            return;
+        }
+        for (int32_t c = 0; c < NC; ++c)
+            this->ra[c] = regular(h, x[c], this->ra[c]);
+    }
+
+    // end of a line: a run that reaches the end of the line (reference src/scan_encoder.hpp:62-68)
+    JLS_HD void end_line()
+    {
+        if (run_count != 0)
+        {
+            fast_encode_run_length(bw, this->run_index, run_count, true);
+            run_count = 0;
+        }
+    }
+
+    JLS_HD uint32_t finish() { return bw.finish(); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoder
+// ---------------------------------------------------------------------------------------------------------------------
+template<int NC, bool LOSSLESS>
+struct FastLineDecoder : FastLineState<NC>
+{
+    FastReader br;
+    int32_t run_left;    // pixels of the current run still to be output
+    bool need_interrupt; // a run-interruption pixel follows the current run
+    bool bad;
+
+    JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, const uint8_t* begin_, const uint8_t* end_)
+    {
+        this->begin_interval(h, ctx, stride);
+        br.init(begin_, end_);
+        run_left = 0;
+        need_interrupt = false;
+        bad = false;
+    }
+
+    JLS_HD void begin_line()
+    {
+        FastLineState<NC>::begin_line();
+        run_left = 0;
+        need_interrupt = false;
+    }
+
+    // reference src/scan_decoder_core.hpp:38-69
+    JLS_HD int32_t regular(const HotParams& h, int32_t ra_value)
+    {
+        const int32_t q = FastLineState<NC>::context_index(h, ra_value);
+        this->select_context(q);
+        RegularContext& c = this->cached;
+        const bool negative = NC == 1 || q != 0;
+        const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
+        int32_t k = golomb_parameter(c.a, c.n);
+        if (JLS_UNLIKELY(k >= 16)) // reference src/regular_mode_context.hpp:107-108
+        {
+            bad = true;
+            k = 15;
+        }
+        int32_t e = unmap_error_value(br.get_golomb(h, k, h.limit - h.qbpp - 1, bad));
+        if (k == 0)
+            e ^= (LOSSLESS || h.near == 0) ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
+        fast_update_context<LOSSLESS>(h, c, e);
+        // the reference's sanity checks (src/scan_decoder_core.hpp:57-58, src/regular_mode_context.hpp:52-54)
+        bad = bad || iabs(e) > 65535 || c.a >= 65536 * 256 || iabs(c.b) >= 65536 * 256;
+        return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
+    }
+
+    // reference src/scan_decoder_core.hpp:72-100
+    JLS_HD void interruption(const HotParams& h)
+    {
+        RunContext& c = this->run_context;
+        for (int32_t i = 0; i < NC; ++i)
+        {
+            const int32_t ri_type = NC == 1 ? 1 : 0;
+            const int32_t k = run_golomb_parameter(c, ri_type);
+            const int32_t e_mapped = br.get_golomb(h, k, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1, bad);
+            const int32_t e = run_error_value(c, e_mapped + ri_type, k);
+            update_run_context(c, e, e_mapped, ri_type, h.reset);
+            if (NC == 1)
+                this->ra[i] = fast_reconstruct<LOSSLESS>(h, this->ra[i], e);
+            else
+                this->ra[i] = fast_reconstruct<LOSSLESS>(h, 0, e * sign_of(-this->ra[i]));
+        }
+        if (this->run_index > 0)
+            --this->run_index;
+        need_interrupt = false;
+    }
+
+    // Decodes one pixel into this->ra. `remaining` = pixels left in the line including this one.
+    JLS_HD void pixel(const HotParams& h, int32_t remaining)
+    {
+        if (JLS_UNLIKELY(run_left > 0))
+        {
+            --run_left;
+            return;
+        }
+        if (JLS_UNLIKELY(need_interrupt))
+        {
+            interruption(h);
+            return;
+        }
+        if (JLS_UNLIKELY(this->in_run_mode(h)))
+        {
+            const int32_t length = fast_decode_run_length(br, this->run_index, remaining);
+            if (length < 0)
+            {
+                bad = true; // reference scan_decoder_impl.hpp:328-329
+                return;
+            }
+            need_interrupt = length != remaining;
+            if (length > 0)
+            {
+                run_left = length - 1;
+                return;
+            }
+            interruption(h);
+            return;
+        }
+        for (int32_t c = 0; c < NC; ++c)
+            this->ra[c] = regular(h, this->ra[c]);
+    }
+};
+
+} // namespace jls

@@ -5,7 +5,7 @@
 // context storage and the atomic error reporting.
 #pragma once
 
-#include "jls_codec.cuh"
+#include "jls_fast.cuh"
 
 namespace jls {
 
@@ -30,55 +30,108 @@ JLS_HD int32_t load_line_component(const CodecParams& p, const uint8_t* line, in
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Fast path, restart interval = 1 line
+// Fast path, restart interval = 1 line.  S = sample type of the caller's buffer (uint8_t / uint16_t).
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS>
+// Tells the compiler a pointer is a global-memory address (so it emits LDG/STG instead of generic LD/ST).
+JLS_HD void assume_global(const void* pointer)
+{
+#if defined(__CUDA_ARCH__)
+    __builtin_assume(__isGlobal(pointer));
+#else
+    (void)pointer;
+#endif
+}
+
+template<typename S>
+JLS_HD int32_t fast_load(const S* line, int32_t index)
+{
+#if defined(__CUDA_ARCH__)
+    return static_cast<int32_t>(__ldg(line + index));
+#else
+    return static_cast<int32_t>(line[index]);
+#endif
+}
+
+// pixel x of a caller line -> NC internal samples: masks unused high bits, or applies the forward colour transform
+// (the transforming variants do not mask, reference src/copy_to_line_buffer.hpp:234-246)
+template<int NC, typename S>
+JLS_HD void fast_load_pixel(const CodecParams& p, const HotParams& h, const S* line, int32_t x, int32_t (&v)[NC])
+{
+    for (int32_t c = 0; c < NC; ++c)
+        v[c] = fast_load(line, x * NC + c);
+    if (NC == 3 && p.transform != 0)
+    {
+        color_forward(p.transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
+    }
+    else if (h.bits != static_cast<int32_t>(8 * sizeof(S)))
+    {
+        for (int32_t c = 0; c < NC; ++c)
+            v[c] &= h.maxval;
+    }
+}
+
+template<int NC, typename S>
+JLS_HD void fast_store_pixel(const CodecParams& p, S* line, int32_t x, const int32_t (&v)[NC])
+{
+    int32_t o[NC];
+    for (int32_t c = 0; c < NC; ++c)
+        o[c] = v[c];
+    if (NC == 3 && p.transform != 0)
+        color_inverse(p.transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, o[0], o[NC > 1 ? 1 : 0], o[NC > 2 ? 2 : 0]);
+    for (int32_t c = 0; c < NC; ++c)
+        line[x * NC + c] = static_cast<S>(o[c]);
+}
+
+// LINE_ILV: the interval holds one line of each of p.components components (line interleave); NC must be 1 then.
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV>
 JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
                                            RegularContext* contexts, int32_t context_stride, size_t slot_bytes)
 {
+    const HotParams h = make_hot_params(p);
     FastLineEncoder<NC, LOSSLESS> enc;
-    enc.begin(p, contexts, context_stride, job.slots + static_cast<size_t>(interval) * slot_bytes, slot_bytes);
-    const uint8_t* line = job.pixels_in + static_cast<size_t>(interval) * job.stride;
+    uint8_t* slot = job.slots + static_cast<size_t>(interval) * slot_bytes;
+    assume_global(slot);
+    enc.begin(h, contexts, context_stride, slot);
+    const S* line = reinterpret_cast<const S*>(job.pixels_in + static_cast<size_t>(interval) * job.stride);
     const int32_t width = p.width;
 
-    bool coded = false;
-    if constexpr (NC == 1)
+    if constexpr (LINE_ILV)
     {
-        if (p.interleave == ilv_line)
+        // one line of every component forms the interval; contexts are shared, the run index restarts per component
+        // (reference src/scan_decoder_impl.hpp:76-117,122-127)
+        static_assert(NC == 1, "line interleave codes scalar lines");
+        const uint8_t* bytes = reinterpret_cast<const uint8_t*>(line);
+        for (int32_t c = 0; c < p.components; ++c)
         {
-            // one line of every component forms the interval; contexts are shared, the run index restarts per component
-            // (reference src/scan_decoder_impl.hpp:76-117,122-127)
-            for (int32_t c = 0; c < p.components; ++c)
+            enc.begin_line();
+            for (int32_t x = 0; x < width; ++x)
             {
-                enc.begin_line();
-                enc.run_count = 0;
-                for (int32_t x = 0; x < width; ++x)
-                {
-                    const int32_t v[1] = {load_line_component(p, line, x, c)};
-                    enc.pixel(p, v, x == width - 1);
-                }
+                const int32_t v[1] = {load_line_component(p, bytes, x, c)};
+                enc.pixel(h, v);
             }
-            coded = true;
+            enc.end_line();
         }
     }
-    if (!coded)
+    else
     {
         for (int32_t x = 0; x < width; ++x)
         {
             int32_t v[NC];
-            load_pixel<NC>(p, line, x, v);
-            enc.pixel(p, v, x == width - 1);
+            fast_load_pixel<NC, S>(p, h, line, x, v);
+            enc.pixel(h, v);
         }
+        enc.end_line();
     }
 
     IntervalResult result;
     result.bytes = enc.finish();
-    result.errc = enc.bw.overflow ? err_destination_too_small : (enc.bad ? err_invalid_data : err_none);
+    result.errc = err_none; // the slot is large enough by construction; invalid states cannot arise from valid samples
     return result;
 }
 
 // What the reference checks when an interval / the scan ends (src/scan_decoder.hpp:71-89,335-349).
-JLS_HD int32_t interval_end_status(const CodecParams& p, const BitReader& br, bool bad, uint32_t interval,
+template<typename Reader>
+JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool bad, uint32_t interval,
                                    bool closing_marker_found = true)
 {
     if (bad || br.overrun())
@@ -98,7 +151,7 @@ JLS_HD int32_t interval_end_status(const CodecParams& p, const BitReader& br, bo
     return br.unread_bytes() > 7 ? err_restart_marker_not_found : err_none;
 }
 
-template<int NC, bool LOSSLESS>
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV>
 JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
                                            RegularContext* contexts, int32_t context_stride)
 {
@@ -114,24 +167,26 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
     if (begin > end)
         return result;
 
+    const HotParams h = make_hot_params(p);
     FastLineDecoder<NC, LOSSLESS> dec;
-    dec.begin(p, contexts, context_stride, job.stream_in + begin, job.stream_in + end);
-    uint8_t* line = job.pixels_out + static_cast<size_t>(interval) * job.stride;
+    dec.begin(h, contexts, context_stride, job.stream_in + begin, job.stream_in + end);
+    S* line = reinterpret_cast<S*>(job.pixels_out + static_cast<size_t>(interval) * job.stride);
+    assume_global(line);
     const int32_t width = p.width;
 
-    bool coded = false;
-    if constexpr (NC == 1)
+    if constexpr (LINE_ILV)
     {
-        if (p.interleave == ilv_line)
+        static_assert(NC == 1, "line interleave codes scalar lines");
         {
             const int32_t nc = p.components;
+            uint8_t* bytes = reinterpret_cast<uint8_t*>(line);
             for (int32_t c = 0; c < nc; ++c)
             {
                 dec.begin_line();
                 for (int32_t x = 0; x < width; ++x)
                 {
-                    dec.pixel(p, width - x);
-                    store_sample(line, x * nc + c, p.sample_bytes, dec.ra[0]);
+                    dec.pixel(h, width - x);
+                    line[x * nc + c] = static_cast<S>(dec.ra[0]);
                 }
             }
             if (nc == 3 && p.transform != 0)
@@ -141,19 +196,18 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
                 {
                     int32_t v[3];
                     for (int32_t c = 0; c < 3; ++c)
-                        v[c] = load_sample(line, x * 3 + c, p.sample_bytes);
-                    store_pixel<3>(p, line, x, v);
+                        v[c] = load_sample(bytes, x * 3 + c, p.sample_bytes);
+                    store_pixel<3>(p, bytes, x, v);
                 }
             }
-            coded = true;
         }
     }
-    if (!coded)
+    else
     {
         for (int32_t x = 0; x < width; ++x)
         {
-            dec.pixel(p, width - x);
-            store_pixel<NC>(p, line, x, dec.ra);
+            dec.pixel(h, width - x);
+            fast_store_pixel<NC, S>(p, line, x, dec.ra);
         }
     }
     result.errc = interval_end_status(p, dec.br, dec.bad, interval, closing_marker_found);

@@ -36,7 +36,7 @@ __device__ __forceinline__ void report_error(const ScanJob& job, uint32_t interv
 // Fast path, restart interval = 1 line: one thread per line, a warp holds 32 consecutive lines.  The five regular
 // contexts of a thread live in shared memory as [context][thread] so that a warp-wide 16-byte access is conflict free.
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS>
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV>
 __global__ void __launch_bounds__(fast_block_threads)
     k_encode_fast(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
@@ -46,13 +46,13 @@ __global__ void __launch_bounds__(fast_block_threads)
     if (interval >= p.interval_count)
         return;
     const IntervalResult r =
-        encode_interval_fast<NC, LOSSLESS>(p, job, interval, contexts + threadIdx.x, fast_block_threads, slot_bytes);
+        encode_interval_fast<NC, LOSSLESS, S, LINE_ILV>(p, job, interval, contexts + threadIdx.x, fast_block_threads, slot_bytes);
     job.interval_bytes[interval] = r.bytes;
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
 }
 
-template<int NC, bool LOSSLESS>
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV>
 __global__ void __launch_bounds__(fast_block_threads)
     k_decode_fast(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
 {
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     const uint32_t interval = blockIdx.x * fast_block_threads + threadIdx.x;
     if (interval >= p.interval_count)
         return;
-    const IntervalResult r = decode_interval_fast<NC, LOSSLESS>(p, job, interval, contexts + threadIdx.x, fast_block_threads);
+    const IntervalResult r = decode_interval_fast<NC, LOSSLESS, S, LINE_ILV>(p, job, interval, contexts + threadIdx.x, fast_block_threads);
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
 }
@@ -454,20 +454,32 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
     {
         const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
         const dim3 block(fast_block_threads);
+        const bool wide = p.sample_bytes == 2;
+#define JLS_LAUNCH_ENCODE(NC, LL, LINE)                                                                                \
+    JLS_TRY(wide ? launch(k_encode_fast<NC, LL, uint16_t, LINE>, grid, block, stream, p, device_jobs, slot_bytes)      \
+                 : launch(k_encode_fast<NC, LL, uint8_t, LINE>, grid, block, stream, p, device_jobs, slot_bytes))
         if (p.interleave == ilv_sample)
         {
             if (lossless)
-                JLS_TRY(launch(k_encode_fast<3, true>, grid, block, stream, p, device_jobs, slot_bytes));
+                JLS_LAUNCH_ENCODE(3, true, false);
             else
-                JLS_TRY(launch(k_encode_fast<3, false>, grid, block, stream, p, device_jobs, slot_bytes));
+                JLS_LAUNCH_ENCODE(3, false, false);
+        }
+        else if (p.interleave == ilv_line)
+        {
+            if (lossless)
+                JLS_LAUNCH_ENCODE(1, true, true);
+            else
+                JLS_LAUNCH_ENCODE(1, false, true);
         }
         else
         {
             if (lossless)
-                JLS_TRY(launch(k_encode_fast<1, true>, grid, block, stream, p, device_jobs, slot_bytes));
+                JLS_LAUNCH_ENCODE(1, true, false);
             else
-                JLS_TRY(launch(k_encode_fast<1, false>, grid, block, stream, p, device_jobs, slot_bytes));
+                JLS_LAUNCH_ENCODE(1, false, false);
         }
+#undef JLS_LAUNCH_ENCODE
     }
     else
     {
@@ -507,20 +519,32 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
     {
         const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
         const dim3 block(fast_block_threads);
+        const bool wide = p.sample_bytes == 2;
+#define JLS_LAUNCH_DECODE(NC, LL, LINE)                                                                                \
+    JLS_TRY(wide ? launch(k_decode_fast<NC, LL, uint16_t, LINE>, grid, block, stream, p, device_jobs)                  \
+                 : launch(k_decode_fast<NC, LL, uint8_t, LINE>, grid, block, stream, p, device_jobs))
         if (p.interleave == ilv_sample)
         {
             if (lossless)
-                JLS_TRY(launch(k_decode_fast<3, true>, grid, block, stream, p, device_jobs));
+                JLS_LAUNCH_DECODE(3, true, false);
             else
-                JLS_TRY(launch(k_decode_fast<3, false>, grid, block, stream, p, device_jobs));
+                JLS_LAUNCH_DECODE(3, false, false);
+        }
+        else if (p.interleave == ilv_line)
+        {
+            if (lossless)
+                JLS_LAUNCH_DECODE(1, true, true);
+            else
+                JLS_LAUNCH_DECODE(1, false, true);
         }
         else
         {
             if (lossless)
-                JLS_TRY(launch(k_decode_fast<1, true>, grid, block, stream, p, device_jobs));
+                JLS_LAUNCH_DECODE(1, true, false);
             else
-                JLS_TRY(launch(k_decode_fast<1, false>, grid, block, stream, p, device_jobs));
+                JLS_LAUNCH_DECODE(1, false, false);
         }
+#undef JLS_LAUNCH_DECODE
     }
     else
     {

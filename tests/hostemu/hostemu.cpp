@@ -50,12 +50,15 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
         IntervalResult r;
         if (fast)
         {
+#define HOSTEMU_ENCODE(NC, LL, LINE)                                                                                       \
+    (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1, slot_bytes)             \
+                         : encode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1, slot_bytes))
             if (p.interleave == ilv_sample)
-                r = lossless ? encode_interval_fast<3, true>(p, job, i, contexts, 1, slot_bytes)
-                             : encode_interval_fast<3, false>(p, job, i, contexts, 1, slot_bytes);
+                r = lossless ? HOSTEMU_ENCODE(3, true, false) : HOSTEMU_ENCODE(3, false, false);
+            else if (p.interleave == ilv_line)
+                r = lossless ? HOSTEMU_ENCODE(1, true, true) : HOSTEMU_ENCODE(1, false, true);
             else
-                r = lossless ? encode_interval_fast<1, true>(p, job, i, contexts, 1, slot_bytes)
-                             : encode_interval_fast<1, false>(p, job, i, contexts, 1, slot_bytes);
+                r = lossless ? HOSTEMU_ENCODE(1, true, false) : HOSTEMU_ENCODE(1, false, false);
         }
         else
         {
@@ -136,10 +139,15 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
         IntervalResult r;
         if (fast)
         {
+#define HOSTEMU_DECODE(NC, LL, LINE)                                                                                       \
+    (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1)                         \
+                         : decode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1))
             if (p.interleave == ilv_sample)
-                r = lossless ? decode_interval_fast<3, true>(p, job, i, contexts, 1) : decode_interval_fast<3, false>(p, job, i, contexts, 1);
+                r = lossless ? HOSTEMU_DECODE(3, true, false) : HOSTEMU_DECODE(3, false, false);
+            else if (p.interleave == ilv_line)
+                r = lossless ? HOSTEMU_DECODE(1, true, true) : HOSTEMU_DECODE(1, false, true);
             else
-                r = lossless ? decode_interval_fast<1, true>(p, job, i, contexts, 1) : decode_interval_fast<1, false>(p, job, i, contexts, 1);
+                r = lossless ? HOSTEMU_DECODE(1, true, false) : HOSTEMU_DECODE(1, false, false);
         }
         else
         {
