@@ -171,6 +171,22 @@ def cpu_reference_step(ref, frames_np, workload, threads, buffers=None):
     return time.perf_counter() - t0
 
 
+def effective_cpus():
+    """CPUs this process may really use: min(os.cpu_count(), scheduler affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def host_frames(workload, count, seed=1234):
     """numpy S_smooth frames for the CPU arm (cheap generator shared by `count` frames with different noise)."""
     w, h, bits, cc, _, _, _ = WORKLOADS[workload]
@@ -199,7 +215,7 @@ def run_reference_arm(args):
     from charls_b200.capi import CharlsLibrary
 
     ref = CharlsLibrary(REF_LIB, extensions=False)
-    threads = os.cpu_count() or 1
+    threads = effective_cpus()
     frames = host_frames(args.workload, min(threads, 8))
     frames = [frames[i % len(frames)] for i in range(threads)]  # one frame per thread per step
     buffers = {}
@@ -364,7 +380,7 @@ def run_gpu_arm(args):
         streams_host = torch.empty((n, codec.stream_capacity), dtype=torch.uint8, pin_memory=True)
         out_host = torch.empty_like(frames_host, pin_memory=True)
         torch.cuda.synchronize()
-        threads = max(1, min(args.e2e_threads, os.cpu_count() or 1))
+        threads = max(1, min(args.e2e_threads, effective_cpus()))
         for _ in range(3):
             e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads)
         if world > 1:
@@ -416,7 +432,7 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu and os.path.exists(REF_LIB):
         ref = capi.CharlsLibrary(REF_LIB, extensions=False)
-        threads = os.cpu_count() or 1
+        threads = effective_cpus()
         hf = host_frames(args.workload, min(threads, 4))
         hf = [hf[i % len(hf)] for i in range(threads)]
         buffers = {}

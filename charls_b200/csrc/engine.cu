@@ -258,7 +258,7 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     jobs[0].stream_out = static_cast<uint8_t*>(stream_buffer_.data);
     jobs[0].stream_out_capacity = device_capacity;
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_));
-    JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, events_));
+    JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, events_, true));
     JLS_CHECK(fetch_outcomes(1, stream_));
     read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
@@ -313,7 +313,7 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream_));
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), 1, remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                           static_cast<uint8_t*>(marker_codes_.data), stream_, events_));
+                           static_cast<uint8_t*>(marker_codes_.data), stream_, events_, true));
     JLS_CHECK(fetch_outcomes(1, stream_));
     read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
@@ -346,11 +346,13 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     std::memcpy(host_prefixes_.data, header, header_size);
     JLS_CUDA(cudaMemcpyAsync(header_.data, host_prefixes_.data, header_size, cudaMemcpyHostToDevice, stream));
 
+    bool word_aligned = stride % 4 == 0;
     std::vector<ScanJob> jobs(count);
     for (size_t i = 0; i < count; ++i)
     {
         ScanJob& job = jobs[i];
         job = ScanJob{};
+        word_aligned = word_aligned && reinterpret_cast<uintptr_t>(frames[i].pixels) % 4 == 0;
         job.pixels_in = frames[i].pixels;
         job.stride = stride;
         const bool room = frames[i].stream_capacity >= header_size + 2;
@@ -359,7 +361,7 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     }
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream));
     const ScanJob* device_jobs = static_cast<const ScanJob*>(job_table_.data);
-    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream, events_));
+    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream, events_, word_aligned));
     JLS_CUDA(launch_wrap_frames(device_jobs, static_cast<const uint8_t*>(header_.data), static_cast<uint32_t>(header_size),
                                 static_cast<uint32_t>(count), stream));
     JLS_CHECK(fetch_outcomes(count, stream));
@@ -419,11 +421,13 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     const uint64_t launches_before = kernel_launch_count();
 
     size_t max_remaining = 0;
+    bool word_aligned = stride % 4 == 0;
     std::vector<ScanJob> jobs(count);
     for (size_t i = 0; i < count; ++i)
     {
         ScanJob& job = jobs[i];
         job = ScanJob{};
+        word_aligned = word_aligned && reinterpret_cast<uintptr_t>(frames[i].pixels) % 4 == 0;
         job.pixels_out = frames[i].pixels;
         job.stride = stride;
         job.stream_in = frames[i].stream + frames[i].scan_offset;
@@ -437,7 +441,7 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream));
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), static_cast<uint32_t>(count), max_remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                           static_cast<uint8_t*>(marker_codes_.data), stream, events_));
+                           static_cast<uint8_t*>(marker_codes_.data), stream, events_, word_aligned));
     JLS_CHECK(fetch_outcomes(count, stream));
     read_coder_time();
     last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);

@@ -272,8 +272,10 @@ struct FastReader
     int32_t remaining;    // real bytes not yet moved into the cache (may go negative)
     int32_t guard;        // > 0 while the word after `cur` still holds bytes of the interval
     uint32_t prev_ff;
+    uint32_t bad;         // malformed code word seen
     const uint32_t* wptr; // aligned word that holds the next byte to fetch
     uint32_t cur;         // *wptr
+    uint32_t ahead;       // wptr[1], loaded one refill early so that its latency is hidden behind ~8 pixels of work
     uint32_t shift;       // 8 * (offset of the next byte inside *wptr)
 
     JLS_HD void init(const uint8_t* begin, const uint8_t* end)
@@ -288,7 +290,9 @@ struct FastReader
         const int32_t offset = static_cast<int32_t>(address & 3U);
         shift = static_cast<uint32_t>(offset) * 8U;
         guard = remaining - (4 - offset);
+        bad = 0;
         cur = remaining > 0 ? *wptr : 0U;
+        ahead = guard > 0 ? wptr[1] : 0U;
         refill();
     }
 
@@ -304,11 +308,11 @@ struct FastReader
 
     JLS_HD void refill_once() // valid <= 32 on entry
     {
-        const uint32_t next = guard > 0 ? wptr[1] : 0U;
-        const uint32_t w = bswap32(funnel_r(cur, next, shift)); // the next four bytes, first one on top
-        cur = next;
+        const uint32_t w = bswap32(funnel_r(cur, ahead, shift)); // the next four bytes, first one on top
+        cur = ahead;
         ++wptr;
         guard -= 4;
+        ahead = guard > 0 ? wptr[1] : 0U; // needed only at the next refill
         if (JLS_LIKELY(remaining >= 4 && (prev_ff | has_ff_byte(w)) == 0))
         {
             cache |= static_cast<uint64_t>(w) << (32 - valid);
@@ -351,7 +355,7 @@ struct FastReader
     }
 
     // limited-length Golomb code (reference src/scan_decoder.hpp:113-125,203-217); `bad` on a malformed code
-    JLS_HD int32_t get_golomb(const HotParams& h, int32_t k, int32_t escape, bool& bad)
+    JLS_HD int32_t get_golomb(const HotParams& h, int32_t k, int32_t escape)
     {
         if (valid <= 32)
             refill();
@@ -384,7 +388,7 @@ struct FastReader
             valid = 0;
             if (overrun()) // ran off the end of the interval inside a unary code (the reference: invalid_data)
             {
-                bad = true;
+                bad = 1;
                 return 0;
             }
         }
@@ -514,7 +518,7 @@ struct FastLineEncoder : FastLineState<NC>
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
         const int32_t e = fast_error_value<LOSSLESS>(h, negative ? pv - x : x - pv);
         const int32_t correction = (LOSSLESS ? k : (k | h.near)) == 0 ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
-        bw.put_golomb(h, k, map_error_value(correction ^ e), h.limit - h.qbpp - 1);
+        bw.put_golomb(h, k, map_error_value(correction ^ e), h.escape);
         fast_update_context<LOSSLESS>(h, c, e);
         return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
     }
@@ -593,7 +597,6 @@ struct FastLineDecoder : FastLineState<NC>
     FastReader br;
     int32_t run_left;    // pixels of the current run still to be output
     bool need_interrupt; // a run-interruption pixel follows the current run
-    bool bad;
 
     JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, const uint8_t* begin_, const uint8_t* end_)
     {
@@ -601,8 +604,9 @@ struct FastLineDecoder : FastLineState<NC>
         br.init(begin_, end_);
         run_left = 0;
         need_interrupt = false;
-        bad = false;
     }
+
+    JLS_HD bool bad() const { return br.bad != 0; }
 
     JLS_HD void begin_line()
     {
@@ -622,15 +626,16 @@ struct FastLineDecoder : FastLineState<NC>
         int32_t k = golomb_parameter(c.a, c.n);
         if (JLS_UNLIKELY(k >= 16)) // reference src/regular_mode_context.hpp:107-108
         {
-            bad = true;
+            br.bad = 1;
             k = 15;
         }
-        int32_t e = unmap_error_value(br.get_golomb(h, k, h.limit - h.qbpp - 1, bad));
+        int32_t e = unmap_error_value(br.get_golomb(h, k, h.escape));
         if (k == 0)
             e ^= (LOSSLESS || h.near == 0) ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
         fast_update_context<LOSSLESS>(h, c, e);
         // the reference's sanity checks (src/scan_decoder_core.hpp:57-58, src/regular_mode_context.hpp:52-54)
-        bad = bad || iabs(e) > 65535 || c.a >= 65536 * 256 || iabs(c.b) >= 65536 * 256;
+        if (JLS_UNLIKELY(iabs(e) > 65535 || c.a >= 65536 * 256 || iabs(c.b) >= 65536 * 256))
+            br.bad = 1;
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }
 
@@ -642,7 +647,7 @@ struct FastLineDecoder : FastLineState<NC>
         {
             const int32_t ri_type = NC == 1 ? 1 : 0;
             const int32_t k = run_golomb_parameter(c, ri_type);
-            const int32_t e_mapped = br.get_golomb(h, k, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1, bad);
+            const int32_t e_mapped = br.get_golomb(h, k, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
             const int32_t e = run_error_value(c, e_mapped + ri_type, k);
             update_run_context(c, e, e_mapped, ri_type, h.reset);
             if (NC == 1)
@@ -673,7 +678,7 @@ struct FastLineDecoder : FastLineState<NC>
             const int32_t length = fast_decode_run_length(br, this->run_index, remaining);
             if (length < 0)
             {
-                bad = true; // reference scan_decoder_impl.hpp:328-329
+                br.bad = 1; // reference scan_decoder_impl.hpp:328-329
                 return;
             }
             need_interrupt = length != remaining;

@@ -210,7 +210,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
             fast_store_pixel<NC, S>(p, line, x, dec.ra);
         }
     }
-    result.errc = interval_end_status(p, dec.br, dec.bad, interval, closing_marker_found);
+    result.errc = interval_end_status(p, dec.br, dec.bad(), interval, closing_marker_found);
     return result;
 }
 

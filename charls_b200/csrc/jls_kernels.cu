@@ -13,6 +13,7 @@
 #include "jls_kernels.hpp"
 
 #include "jls_interval.cuh"
+#include "jls_tile.cuh"
 
 #include <cuda_runtime.h>
 
@@ -64,6 +65,176 @@ __global__ void __launch_bounds__(fast_block_threads)
     const IntervalResult r = decode_interval_fast<NC, LOSSLESS, S, LINE_ILV>(p, job, interval, contexts + threadIdx.x, fast_block_threads);
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path with shared-memory tiles (jls_tile.cuh): the same per-line codec, but the samples travel between HBM and the
+// lanes as coalesced [32 lines x 64/96 bytes] tiles instead of per-lane byte accesses.  Needs 4-byte aligned rows.
+// ---------------------------------------------------------------------------------------------------------------------
+template<int NC>
+struct TileShape
+{
+    static constexpr int words = NC == 3 ? 24 : 16; // 96 bytes hold whole pixels for 3 x 8 and 3 x 16 bit
+    static constexpr int stride_words = words + 1;
+};
+
+template<int NC, bool LOSSLESS, typename S>
+__global__ void __launch_bounds__(fast_block_threads)
+    k_encode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
+{
+    constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
+    constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
+    constexpr int warps = fast_block_threads / 32;
+    __shared__ RegularContext contexts[5 * fast_block_threads];
+    __shared__ uint32_t tiles[warps][2][32 * SW];
+
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t first_line = (blockIdx.x * warps + warp) * 32U;
+    if (first_line >= p.interval_count)
+        return; // whole warp
+    const uint32_t interval = first_line + lane;
+    const bool active = interval < p.interval_count;
+
+    const HotParams h = make_hot_params(p);
+    FastLineEncoder<NC, LOSSLESS> enc;
+    uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
+    assume_global(slot);
+    enc.begin(h, contexts + threadIdx.x, fast_block_threads, slot);
+
+    const uint8_t* pixels = job.pixels_in;
+    assume_global(pixels);
+    const size_t stride = job.stride;
+    const int32_t width = p.width;
+    const int32_t row_bytes = width * NC * static_cast<int32_t>(sizeof(S));
+    const int32_t tile_count = (row_bytes + TW * 4 - 1) / (TW * 4);
+    const uint32_t last_line = p.interval_count - 1;
+    const int32_t transform = p.transform;
+    const bool mask_needed = h.bits != static_cast<int32_t>(8 * sizeof(S));
+
+    tile_load_async<TW>(tiles[warp][0], pixels, stride, first_line, last_line, row_bytes, 0, lane);
+    for (int32_t t = 0; t < tile_count; ++t)
+    {
+        if (t + 1 < tile_count)
+        {
+            tile_load_async<TW>(tiles[warp][(t + 1) & 1], pixels, stride, first_line, last_line, row_bytes, t + 1, lane);
+            cp_async_wait<1>();
+        }
+        else
+        {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        if (active)
+        {
+            const S* row = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
+            const int32_t count = min(pixels_per_tile, width - t * pixels_per_tile);
+            for (int32_t i = 0; i < count; ++i)
+            {
+                int32_t v[NC];
+#pragma unroll
+                for (int32_t c = 0; c < NC; ++c)
+                    v[c] = row[i * NC + c];
+                if (NC == 3 && transform != 0)
+                {
+                    color_forward(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
+                }
+                else if (mask_needed)
+                {
+#pragma unroll
+                    for (int32_t c = 0; c < NC; ++c)
+                        v[c] &= h.maxval;
+                }
+                enc.pixel(h, v);
+            }
+        }
+        __syncwarp(); // everybody is done with this buffer before the copy two tiles ahead overwrites it
+    }
+    if (active)
+    {
+        enc.end_line();
+        job.interval_bytes[interval] = enc.finish();
+    }
+}
+
+template<int NC, bool LOSSLESS, typename S>
+__global__ void __launch_bounds__(fast_block_threads)
+    k_decode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
+{
+    constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
+    constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
+    constexpr int warps = fast_block_threads / 32;
+    __shared__ RegularContext contexts[5 * fast_block_threads];
+    __shared__ uint32_t tiles[warps][32 * SW];
+
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t first_line = (blockIdx.x * warps + warp) * 32U;
+    if (first_line >= p.interval_count)
+        return; // whole warp
+    const uint32_t interval = first_line + lane;
+
+    // interval_offset holds 2 entries per interval: [2i] = first byte, [2i+1] = end (first 0xFF of the closing marker)
+    uint64_t begin = 0, end = 0;
+    bool coding = interval < p.interval_count;
+    bool closing_marker_found = true;
+    if (coding)
+    {
+        begin = job.interval_offset[2 * static_cast<size_t>(interval)];
+        end = job.interval_offset[2 * static_cast<size_t>(interval) + 1];
+        closing_marker_found = end != ~0ULL;
+        if (!closing_marker_found)
+            end = job.stream_in_size; // decode what is there (the reference runs dry -> invalid_data)
+        coding = begin != ~0ULL && begin <= end; // else an earlier marker is missing: k_decode_finish reports it
+    }
+    const uint32_t row_mask = __ballot_sync(0xFFFFFFFFU, coding);
+
+    const HotParams h = make_hot_params(p);
+    FastLineDecoder<NC, LOSSLESS> dec;
+    const uint8_t* stream = job.stream_in;
+    assume_global(stream);
+    dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
+
+    uint8_t* pixels = job.pixels_out;
+    assume_global(pixels);
+    const size_t stride = job.stride;
+    const int32_t width = p.width;
+    const int32_t row_bytes = width * NC * static_cast<int32_t>(sizeof(S));
+    const int32_t tile_count = (row_bytes + TW * 4 - 1) / (TW * 4);
+    const int32_t transform = p.transform;
+    uint32_t* tile = tiles[warp];
+
+    for (int32_t t = 0; t < tile_count; ++t)
+    {
+        if (coding)
+        {
+            S* row = reinterpret_cast<S*>(&tile[lane * SW]);
+            const int32_t x0 = t * pixels_per_tile;
+            const int32_t count = min(pixels_per_tile, width - x0);
+            for (int32_t i = 0; i < count; ++i)
+            {
+                dec.pixel(h, width - x0 - i);
+                int32_t v[NC];
+#pragma unroll
+                for (int32_t c = 0; c < NC; ++c)
+                    v[c] = dec.ra[c];
+                if (NC == 3 && transform != 0)
+                    color_inverse(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
+#pragma unroll
+                for (int32_t c = 0; c < NC; ++c)
+                    row[i * NC + c] = static_cast<S>(v[c]);
+            }
+        }
+        __syncwarp();
+        tile_store<TW>(tile, pixels, stride, first_line, row_mask, row_bytes, t, lane);
+        __syncwarp();
+    }
+    if (coding)
+    {
+        const int32_t errc = interval_end_status(p, dec.br, dec.bad(), interval, closing_marker_found);
+        if (errc != err_none)
+            report_error(job, interval, errc);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -444,7 +615,7 @@ size_t marker_blocks_for(size_t stream_bytes) noexcept
     } while (0)
 
 cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
-                          cudaStream_t stream, cudaEvent_t* coder_events)
+                          cudaStream_t stream, cudaEvent_t* coder_events, bool rows_word_aligned)
 {
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
     const bool lossless = p.near == 0;
@@ -458,7 +629,29 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
 #define JLS_LAUNCH_ENCODE(NC, LL, LINE)                                                                                \
     JLS_TRY(wide ? launch(k_encode_fast<NC, LL, uint16_t, LINE>, grid, block, stream, p, device_jobs, slot_bytes)      \
                  : launch(k_encode_fast<NC, LL, uint8_t, LINE>, grid, block, stream, p, device_jobs, slot_bytes))
-        if (p.interleave == ilv_sample)
+#define JLS_LAUNCH_ENCODE_TILED(NC, LL)                                                                                \
+    JLS_TRY(wide ? launch(k_encode_tiled<NC, LL, uint16_t>, grid, block, stream, p, device_jobs, slot_bytes)           \
+                 : launch(k_encode_tiled<NC, LL, uint8_t>, grid, block, stream, p, device_jobs, slot_bytes))
+        const bool tiled = rows_word_aligned && p.interleave != ilv_line &&
+                           (static_cast<size_t>(p.width) * (p.interleave == ilv_sample ? 3U : 1U) * p.sample_bytes) % 4U == 0;
+        if (tiled)
+        {
+            if (p.interleave == ilv_sample)
+            {
+                if (lossless)
+                    JLS_LAUNCH_ENCODE_TILED(3, true);
+                else
+                    JLS_LAUNCH_ENCODE_TILED(3, false);
+            }
+            else
+            {
+                if (lossless)
+                    JLS_LAUNCH_ENCODE_TILED(1, true);
+                else
+                    JLS_LAUNCH_ENCODE_TILED(1, false);
+            }
+        }
+        else if (p.interleave == ilv_sample)
         {
             if (lossless)
                 JLS_LAUNCH_ENCODE(3, true, false);
@@ -480,6 +673,7 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
                 JLS_LAUNCH_ENCODE(1, false, false);
         }
 #undef JLS_LAUNCH_ENCODE
+#undef JLS_LAUNCH_ENCODE_TILED
     }
     else
     {
@@ -499,7 +693,7 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
 
 cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
                           uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream,
-                          cudaEvent_t* coder_events)
+                          cudaEvent_t* coder_events, bool rows_word_aligned)
 {
     const uint32_t blocks_per_job = static_cast<uint32_t>(marker_blocks_for(max_stream_bytes));
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
@@ -523,7 +717,29 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
 #define JLS_LAUNCH_DECODE(NC, LL, LINE)                                                                                \
     JLS_TRY(wide ? launch(k_decode_fast<NC, LL, uint16_t, LINE>, grid, block, stream, p, device_jobs)                  \
                  : launch(k_decode_fast<NC, LL, uint8_t, LINE>, grid, block, stream, p, device_jobs))
-        if (p.interleave == ilv_sample)
+#define JLS_LAUNCH_DECODE_TILED(NC, LL)                                                                                \
+    JLS_TRY(wide ? launch(k_decode_tiled<NC, LL, uint16_t>, grid, block, stream, p, device_jobs)                       \
+                 : launch(k_decode_tiled<NC, LL, uint8_t>, grid, block, stream, p, device_jobs))
+        const bool tiled = rows_word_aligned && p.interleave != ilv_line &&
+                           (static_cast<size_t>(p.width) * (p.interleave == ilv_sample ? 3U : 1U) * p.sample_bytes) % 4U == 0;
+        if (tiled)
+        {
+            if (p.interleave == ilv_sample)
+            {
+                if (lossless)
+                    JLS_LAUNCH_DECODE_TILED(3, true);
+                else
+                    JLS_LAUNCH_DECODE_TILED(3, false);
+            }
+            else
+            {
+                if (lossless)
+                    JLS_LAUNCH_DECODE_TILED(1, true);
+                else
+                    JLS_LAUNCH_DECODE_TILED(1, false);
+            }
+        }
+        else if (p.interleave == ilv_sample)
         {
             if (lossless)
                 JLS_LAUNCH_DECODE(3, true, false);
@@ -545,6 +761,7 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
                 JLS_LAUNCH_DECODE(1, false, false);
         }
 #undef JLS_LAUNCH_DECODE
+#undef JLS_LAUNCH_DECODE_TILED
     }
     else
     {

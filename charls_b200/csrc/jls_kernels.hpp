@@ -17,14 +17,15 @@ size_t marker_blocks_for(size_t stream_bytes) noexcept;
 // Encodes `job_count` scans that share the coding parameters `p`.  Afterwards, per job: result[0] = bytes written to
 // stream_out (interval data + RSTm markers), status = first error key (~0 when none).
 // coder_events (optional): two events recorded directly before / after the entropy-coding kernel (the dominant one).
+// rows_word_aligned: every job's sample buffer and stride are multiples of 4 bytes (enables the shared-memory tile kernels).
 cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
-                          cudaStream_t stream, cudaEvent_t* coder_events = nullptr);
+                          cudaStream_t stream, cudaEvent_t* coder_events = nullptr, bool rows_word_aligned = false);
 
 // Decodes `job_count` scans.  block_counts: job_count * marker_blocks_for(max_stream_bytes) uint32; marker_totals:
 // job_count uint32; marker_codes: job_count * interval_count bytes.  Afterwards result[0] = bytes consumed by the scan.
 cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
                           uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream,
-                          cudaEvent_t* coder_events = nullptr);
+                          cudaEvent_t* coder_events = nullptr, bool rows_word_aligned = false);
 
 // Batch encode: writes `header` in front of and EOI behind every frame's entropy-coded data (see k_wrap_frames).
 cudaError_t launch_wrap_frames(const ScanJob* device_jobs, const uint8_t* device_header, uint32_t header_size,

@@ -1,0 +1,74 @@
+// jls_tile.cuh -- warp-cooperative staging of sample rows through shared memory (device only).
+//
+// A warp codes 32 lines in lock step, every lane walking along its own line.  Touching global memory per lane would cost
+// 32 L1 wavefronts per instruction (32 lanes, 32 different lines) -- ncu showed the L1 pipe saturating before the issue
+// slots (profiles/r1_notes.md).  So the warp moves [32 lines x TW words] tiles instead: every copy instruction covers
+// whole 64/96-byte row segments (coalesced), the tile sits in shared memory with rows padded to an odd number of
+// words, and lane r then reads / writes its row with conflict-free LDS/STS (bank = (r * (TW+1) + w) mod 32 is a
+// permutation of the lanes).  Loads are asynchronous (cp.async, SASS LDGSTS) and double buffered: the tile after the
+// one being coded is already in flight, so HBM latency is hidden behind 64 pixels of coding work per lane.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace jls {
+
+__device__ __forceinline__ void cp_async_4(void* smem_destination, const void* global_source, int source_bytes)
+{
+    const unsigned address = static_cast<unsigned>(__cvta_generic_to_shared(smem_destination));
+    // source_bytes == 0: nothing is read, the destination word is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(address), "l"(global_source), "r"(source_bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+template<int PENDING>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
+}
+
+// Starts the copy of tile `tile_index` (TW words of each of the warp's 32 lines) into `tile` ([32][TW + 1] words).
+// Lines past `last_line` repeat the last line (never coded); words past the end of a row are zero-filled.
+template<int TW>
+__device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* pixels, size_t stride, uint32_t first_line,
+                                                uint32_t last_line, int32_t row_bytes, int32_t tile_index, uint32_t lane)
+{
+#pragma unroll 4
+    for (int k = 0; k < TW; ++k)
+    {
+        const uint32_t index = static_cast<uint32_t>(k) * 32U + lane;
+        const uint32_t r = index / TW;
+        const uint32_t w = index - r * TW;
+        const int32_t byte = tile_index * (TW * 4) + static_cast<int32_t>(w) * 4;
+        const bool inside = byte < row_bytes;
+        const uint32_t line = min(first_line + r, last_line);
+        const uint8_t* source = pixels + static_cast<size_t>(line) * stride + (inside ? byte : 0);
+        cp_async_4(tile + r * (TW + 1) + w, source, inside ? 4 : 0);
+    }
+    cp_async_commit();
+}
+
+// Writes tile `tile_index` back: row r goes to line first_line + r if bit r of `row_mask` is set.
+template<int TW>
+__device__ __forceinline__ void tile_store(const uint32_t* tile, uint8_t* pixels, size_t stride, uint32_t first_line,
+                                           uint32_t row_mask, int32_t row_bytes, int32_t tile_index, uint32_t lane)
+{
+#pragma unroll 4
+    for (int k = 0; k < TW; ++k)
+    {
+        const uint32_t index = static_cast<uint32_t>(k) * 32U + lane;
+        const uint32_t r = index / TW;
+        const uint32_t w = index - r * TW;
+        const int32_t byte = tile_index * (TW * 4) + static_cast<int32_t>(w) * 4;
+        if (byte < row_bytes && ((row_mask >> r) & 1U) != 0)
+            *reinterpret_cast<uint32_t*>(pixels + static_cast<size_t>(first_line + r) * stride + byte) = tile[r * (TW + 1) + w];
+    }
+}
+
+} // namespace jls
