@@ -53,8 +53,17 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.a_init = p.a_init;
     h.dq_magic = p.dq_magic;
 #if defined(__CUDA_ARCH__)
-    // keep the hot ones in registers instead of re-reading the constant bank in every iteration
-    asm volatile("" : "+r"(h.t1), "+r"(h.t2), "+r"(h.t3), "+r"(h.reset), "+r"(h.escape), "+r"(h.maxval), "+r"(h.bits));
+    // Keep the hot ones in registers: a value that went through a shuffle is opaque to ptxas, which otherwise re-reads
+    // the constant bank (LDC/LDCU) for every use inside the pixel loop -- 5 to 9 issue slots per pixel (profiles/).
+    const int lane = static_cast<int>(threadIdx.x & 31U);
+    h.t1 = __shfl_sync(0xFFFFFFFFU, h.t1, lane);
+    h.t2 = __shfl_sync(0xFFFFFFFFU, h.t2, lane);
+    h.t3 = __shfl_sync(0xFFFFFFFFU, h.t3, lane);
+    h.near = __shfl_sync(0xFFFFFFFFU, h.near, lane);
+    h.reset = __shfl_sync(0xFFFFFFFFU, h.reset, lane);
+    h.escape = __shfl_sync(0xFFFFFFFFU, h.escape, lane);
+    h.maxval = __shfl_sync(0xFFFFFFFFU, h.maxval, lane);
+    h.bits = __shfl_sync(0xFFFFFFFFU, h.bits, lane);
 #endif
     return h;
 }
@@ -287,6 +296,9 @@ struct FastReader
         remaining = static_cast<int32_t>(end - begin);
         const uintptr_t address = reinterpret_cast<uintptr_t>(begin);
         wptr = reinterpret_cast<const uint32_t*>(address & ~static_cast<uintptr_t>(3));
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isGlobal(wptr));
+#endif
         const int32_t offset = static_cast<int32_t>(address & 3U);
         shift = static_cast<uint32_t>(offset) * 8U;
         guard = remaining - (4 - offset);
@@ -312,6 +324,9 @@ struct FastReader
         cur = ahead;
         ++wptr;
         guard -= 4;
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isGlobal(wptr));
+#endif
         ahead = guard > 0 ? wptr[1] : 0U; // needed only at the next refill
         if (JLS_LIKELY(remaining >= 4 && (prev_ff | has_ff_byte(w)) == 0))
         {
@@ -634,7 +649,8 @@ struct FastLineDecoder : FastLineState<NC>
             e ^= (LOSSLESS || h.near == 0) ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
         fast_update_context<LOSSLESS>(h, c, e);
         // the reference's sanity checks (src/scan_decoder_core.hpp:57-58, src/regular_mode_context.hpp:52-54)
-        if (JLS_UNLIKELY(iabs(e) > 65535 || c.a >= 65536 * 256 || iabs(c.b) >= 65536 * 256))
+        // a >= 0; one test covers a >= 2^24, |b| >= 2^24 and |e| > 65535
+        if (JLS_UNLIKELY((((c.a | iabs(c.b)) >> 24) | (iabs(e) >> 16)) != 0))
             br.bad = 1;
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }

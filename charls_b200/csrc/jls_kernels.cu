@@ -127,14 +127,14 @@ __global__ void __launch_bounds__(fast_block_threads)
         __syncwarp();
         if (active)
         {
-            const S* row = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
-            const int32_t count = min(pixels_per_tile, width - t * pixels_per_tile);
-            for (int32_t i = 0; i < count; ++i)
+            const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
+            const S* const tile_end = sample + min(pixels_per_tile, width - t * pixels_per_tile) * NC;
+            for (; sample != tile_end; sample += NC)
             {
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
-                    v[c] = row[i * NC + c];
+                    v[c] = sample[c];
                 if (NC == 3 && transform != 0)
                 {
                     color_forward(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
@@ -208,12 +208,12 @@ __global__ void __launch_bounds__(fast_block_threads)
     {
         if (coding)
         {
-            S* row = reinterpret_cast<S*>(&tile[lane * SW]);
+            S* sample = reinterpret_cast<S*>(&tile[lane * SW]);
             const int32_t x0 = t * pixels_per_tile;
-            const int32_t count = min(pixels_per_tile, width - x0);
-            for (int32_t i = 0; i < count; ++i)
+            S* const tile_end = sample + min(pixels_per_tile, width - x0) * NC;
+            for (int32_t left = width - x0; sample != tile_end; sample += NC, --left)
             {
-                dec.pixel(h, width - x0 - i);
+                dec.pixel(h, left);
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(fast_block_threads)
                     color_inverse(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
-                    row[i * NC + c] = static_cast<S>(v[c]);
+                    sample[c] = static_cast<S>(v[c]);
             }
         }
         __syncwarp();
