@@ -46,8 +46,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step (128 x 8 GPUs = BASELINE configs[4])")
-    ap.add_argument("--e2e-frames", type=int, default=16)
-    ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-frames", type=int, default=32)
+    ap.add_argument("--e2e-threads", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

@@ -469,6 +469,7 @@ struct FastLineState
     JLS_HD void begin_line()
     {
         run_index = 0;
+#pragma unroll
         for (int32_t c = 0; c < NC; ++c)
             ra[c] = 0;
     }
@@ -494,6 +495,7 @@ struct FastLineState
         if (NC == 1)
             return ra[0] <= h.near;
         int32_t m = ra[0];
+#pragma unroll
         for (int32_t c = 1; c < NC; ++c)
             m = imax(m, ra[c]);
         return m <= h.near;
@@ -555,6 +557,7 @@ struct FastLineEncoder : FastLineState<NC>
         if (JLS_UNLIKELY(this->in_run_mode(h)))
         {
             bool same = true;
+#pragma unroll
             for (int32_t c = 0; c < NC; ++c)
                 same = same && iabs(x[c] - this->ra[c]) <= h.near;
             if (same)
@@ -564,6 +567,7 @@ struct FastLineEncoder : FastLineState<NC>
             }
             fast_encode_run_length(bw, this->run_index, run_count, false);
             run_count = 0;
+#pragma unroll
             for (int32_t c = 0; c < NC; ++c)
             {
                 if (NC == 1)
@@ -586,6 +590,7 @@ struct FastLineEncoder : FastLineState<NC>
                 --this->run_index;
             return;
         }
+#pragma unroll
         for (int32_t c = 0; c < NC; ++c)
             this->ra[c] = regular(h, x[c], this->ra[c]);
     }
@@ -659,6 +664,7 @@ struct FastLineDecoder : FastLineState<NC>
     JLS_HD void interruption(const HotParams& h)
     {
         RunContext& c = this->run_context;
+#pragma unroll
         for (int32_t i = 0; i < NC; ++i)
         {
             const int32_t ri_type = NC == 1 ? 1 : 0;
@@ -706,6 +712,7 @@ struct FastLineDecoder : FastLineState<NC>
             interruption(h);
             return;
         }
+#pragma unroll
         for (int32_t c = 0; c < NC; ++c)
             this->ra[c] = regular(h, this->ra[c]);
     }

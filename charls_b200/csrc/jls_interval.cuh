@@ -364,12 +364,10 @@ JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, con
     return result;
 }
 
-// Which intervals take the fast path: one line per interval; scalar lines (ILV none / line) or 3-component pixels.
+// Which intervals take the fast path: exactly one line per interval (scalar lines or 2..4-component pixels).
 inline bool use_fast_path(const CodecParams& p)
 {
-    if (p.lines_per_interval != 1)
-        return false;
-    return p.interleave != ilv_sample || p.components == 3;
+    return p.lines_per_interval == 1;
 }
 
 } // namespace jls

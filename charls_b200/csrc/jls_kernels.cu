@@ -388,22 +388,56 @@ constexpr int marker_block_threads = 256;
 constexpr int marker_bytes_per_thread = 16;
 constexpr int marker_bytes_per_block = marker_block_threads * marker_bytes_per_thread;
 
-__device__ __forceinline__ uint32_t marker_mask_of_thread(const uint8_t* data, size_t size, size_t first)
+// 0x80 in every byte of x that equals 0xFF (exact, no carries between bytes)
+__device__ __forceinline__ uint32_t ff_bytes(uint32_t x)
 {
-    // bit i set <=> data[first + i] is a marker code byte
-    uint32_t mask = 0;
-    if (first >= size)
-        return 0;
-    uint32_t previous = first > 0 ? data[first - 1] : 0U;
-    const size_t count = min(static_cast<size_t>(marker_bytes_per_thread), size - first);
-    for (size_t i = 0; i < count; ++i)
+    return ((x & 0x7F7F7F7FU) + 0x01010101U) & x & 0x80808080U;
+}
+
+// The 16 stream bytes a thread inspects.  Chunks are laid out on absolute 16-byte boundaries of the buffer so that the
+// interior ones can be fetched with one aligned 128-bit load; bit i of `mask` <=> data[base + i] is a marker code byte.
+struct MarkerChunk
+{
+    uint32_t mask;
+    int64_t base;
+};
+
+__device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t size, size_t chunk_index)
+{
+    const int64_t lead = static_cast<int64_t>(reinterpret_cast<uintptr_t>(data) & 15U);
+    MarkerChunk chunk;
+    chunk.base = static_cast<int64_t>(chunk_index) * marker_bytes_per_thread - lead;
+    chunk.mask = 0;
+    const int64_t n = static_cast<int64_t>(size);
+    if (chunk.base >= n)
+        return chunk;
+    if (chunk.base >= 1 && chunk.base + marker_bytes_per_thread <= n)
     {
-        const uint32_t b = data[first + i];
+        const uint4 q = *reinterpret_cast<const uint4*>(data + chunk.base);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t previous = data[chunk.base - 1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            // byte j of `shifted` is the stream byte in front of byte j of w[i] (little endian: earlier byte = lower bits)
+            const uint32_t shifted = (w[i] << 8) | previous;
+            const uint32_t m = ff_bytes(shifted) & w[i] & ~ff_bytes(w[i]); // 0x80 where FF is followed by >= 0x80, != FF
+            chunk.mask |= (((m >> 7) & 1U) | ((m >> 14) & 2U) | ((m >> 21) & 4U) | ((m >> 28) & 8U)) << (4 * i);
+            previous = w[i] >> 24;
+        }
+        return chunk;
+    }
+    const int64_t begin = chunk.base < 0 ? 0 : chunk.base;
+    const int64_t end = chunk.base + marker_bytes_per_thread < n ? chunk.base + marker_bytes_per_thread : n;
+    uint32_t previous = begin > 0 ? data[begin - 1] : 0U;
+    for (int64_t i = begin; i < end; ++i)
+    {
+        const uint32_t b = data[i];
         if (previous == 0xFFU && b >= 0x80U && b != 0xFFU)
-            mask |= 1U << i;
+            chunk.mask |= 1U << static_cast<uint32_t>(i - chunk.base);
         previous = b;
     }
-    return mask;
+    return chunk;
 }
 
 // grid (blocks, jobs): block_counts[job][block]
@@ -411,9 +445,8 @@ __global__ void __launch_bounds__(marker_block_threads)
     k_marker_count(const ScanJob* __restrict__ jobs, uint32_t* __restrict__ block_counts, uint32_t blocks_per_job)
 {
     const ScanJob& job = jobs[blockIdx.y];
-    const size_t first = static_cast<size_t>(blockIdx.x) * marker_bytes_per_block +
-                         static_cast<size_t>(threadIdx.x) * marker_bytes_per_thread;
-    const uint32_t count = __popc(marker_mask_of_thread(job.stream_in, job.stream_in_size, first));
+    const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
+    const uint32_t count = __popc(marker_chunk(job.stream_in, job.stream_in_size, chunk_index).mask);
     __shared__ uint32_t warp_sums[marker_block_threads / 32];
     uint32_t sum = count;
 #pragma unroll
@@ -460,9 +493,9 @@ __global__ void __launch_bounds__(marker_block_threads)
 {
     __shared__ uint32_t warp_sums[marker_block_threads / 32];
     const ScanJob& job = jobs[blockIdx.y];
-    const size_t first = static_cast<size_t>(blockIdx.x) * marker_bytes_per_block +
-                         static_cast<size_t>(threadIdx.x) * marker_bytes_per_thread;
-    const uint32_t mask = marker_mask_of_thread(job.stream_in, job.stream_in_size, first);
+    const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
+    const MarkerChunk chunk = marker_chunk(job.stream_in, job.stream_in_size, chunk_index);
+    const uint32_t mask = chunk.mask;
     const uint32_t count = __popc(mask);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inclusive = count;
@@ -487,19 +520,23 @@ __global__ void __launch_bounds__(marker_block_threads)
     {
         const uint32_t bit = __ffs(remaining) - 1;
         remaining &= remaining - 1;
-        const size_t code_position = first + bit;
+        const size_t code_position = static_cast<size_t>(chunk.base + bit);
         size_t marker_begin = code_position - 1;
         while (marker_begin > 0 && job.stream_in[marker_begin - 1] == 0xFF) // fill bytes (T.81 B.1.1.2)
             --marker_begin;
         job.interval_offset[2 * static_cast<size_t>(rank) + 1] = marker_begin;
         if (rank + 1 < p.interval_count)
             job.interval_offset[2 * static_cast<size_t>(rank) + 2] = code_position + 1;
-        marker_codes[static_cast<size_t>(blockIdx.y) * p.interval_count + rank] = job.stream_in[code_position];
+        const uint8_t code = job.stream_in[code_position];
+        marker_codes[static_cast<size_t>(blockIdx.y) * p.interval_count + rank] = code;
+        // the first interval_count - 1 markers must be RSTm with m = index mod 8 (reference src/scan_decoder.hpp:335-349)
+        if (rank + 1 < p.interval_count && code != 0xD0U + (rank & 7U))
+            report_error(job, rank, err_restart_marker_not_found);
         ++rank;
     }
 }
 
-// one thread per job: the first interval_count - 1 markers must be RSTm with m = index mod 8; the last one ends the scan
+// one thread per job: bytes consumed by the scan, its closing marker, and the data-ends-early case
 __global__ void k_decode_finish(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
                                 const uint32_t* __restrict__ marker_totals, const uint8_t* __restrict__ marker_codes,
                                 uint32_t job_count)
@@ -510,14 +547,6 @@ __global__ void k_decode_finish(const __grid_constant__ CodecParams p, const Sca
     const ScanJob& job = jobs[j];
     const uint32_t found = marker_totals[j];
     const uint8_t* codes = marker_codes + static_cast<size_t>(j) * p.interval_count;
-    for (uint32_t i = 0; i + 1 < p.interval_count && i < found; ++i)
-    {
-        if (codes[i] != 0xD0U + (i & 7U)) // reference src/scan_decoder.hpp:335-349
-        {
-            report_error(job, i, err_restart_marker_not_found);
-            break;
-        }
-    }
     if (found < p.interval_count)
     {
         // The data ends inside interval `found`.  The reference either ran out of bits while decoding it
@@ -594,6 +623,102 @@ cudaError_t launch(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, Ar
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant selection for the fast path -- the counterpart of the reference's make_scan_codec (src/make_scan_codec.cpp:40-156):
+// components per pixel (1 = scalar lines, 2..4 = sample interleave), lossless or not, 8 / 16 bit containers,
+// tiled (4-byte aligned rows) or per-lane access, line interleave.
+// ---------------------------------------------------------------------------------------------------------------------
+bool rows_tileable(const CodecParams& p, bool rows_word_aligned)
+{
+    const size_t samples_per_pixel = p.interleave == ilv_sample ? static_cast<size_t>(p.components) : 1U;
+    return rows_word_aligned && p.interleave != ilv_line &&
+           (static_cast<size_t>(p.width) * samples_per_pixel * static_cast<size_t>(p.sample_bytes)) % 4U == 0;
+}
+
+template<int NC, bool LL, typename S>
+cudaError_t launch_encode_fast(const CodecParams& p, bool tiled, dim3 grid, dim3 block, cudaStream_t stream,
+                               const ScanJob* jobs, size_t slot_bytes)
+{
+    if (tiled)
+        return launch(k_encode_tiled<NC, LL, S>, grid, block, stream, p, jobs, slot_bytes);
+    if constexpr (NC == 1)
+    {
+        if (p.interleave == ilv_line)
+            return launch(k_encode_fast<1, LL, S, true>, grid, block, stream, p, jobs, slot_bytes);
+    }
+    return launch(k_encode_fast<NC, LL, S, false>, grid, block, stream, p, jobs, slot_bytes);
+}
+
+template<int NC, bool LL, typename S>
+cudaError_t launch_decode_fast(const CodecParams& p, bool tiled, dim3 grid, dim3 block, cudaStream_t stream, const ScanJob* jobs)
+{
+    if (tiled)
+        return launch(k_decode_tiled<NC, LL, S>, grid, block, stream, p, jobs);
+    if constexpr (NC == 1)
+    {
+        if (p.interleave == ilv_line)
+            return launch(k_decode_fast<1, LL, S, true>, grid, block, stream, p, jobs);
+    }
+    return launch(k_decode_fast<NC, LL, S, false>, grid, block, stream, p, jobs);
+}
+
+template<int NC>
+cudaError_t dispatch_encode_nc(const CodecParams& p, bool tiled, dim3 grid, dim3 block, cudaStream_t stream,
+                               const ScanJob* jobs, size_t slot_bytes)
+{
+    const bool wide = p.sample_bytes == 2;
+    if (p.near == 0)
+        return wide ? launch_encode_fast<NC, true, uint16_t>(p, tiled, grid, block, stream, jobs, slot_bytes)
+                    : launch_encode_fast<NC, true, uint8_t>(p, tiled, grid, block, stream, jobs, slot_bytes);
+    return wide ? launch_encode_fast<NC, false, uint16_t>(p, tiled, grid, block, stream, jobs, slot_bytes)
+                : launch_encode_fast<NC, false, uint8_t>(p, tiled, grid, block, stream, jobs, slot_bytes);
+}
+
+template<int NC>
+cudaError_t dispatch_decode_nc(const CodecParams& p, bool tiled, dim3 grid, dim3 block, cudaStream_t stream, const ScanJob* jobs)
+{
+    const bool wide = p.sample_bytes == 2;
+    if (p.near == 0)
+        return wide ? launch_decode_fast<NC, true, uint16_t>(p, tiled, grid, block, stream, jobs)
+                    : launch_decode_fast<NC, true, uint8_t>(p, tiled, grid, block, stream, jobs);
+    return wide ? launch_decode_fast<NC, false, uint16_t>(p, tiled, grid, block, stream, jobs)
+                : launch_decode_fast<NC, false, uint8_t>(p, tiled, grid, block, stream, jobs);
+}
+
+cudaError_t dispatch_encode_fast(const CodecParams& p, bool rows_word_aligned, dim3 grid, dim3 block, cudaStream_t stream,
+                                 const ScanJob* jobs, size_t slot_bytes)
+{
+    const bool tiled = rows_tileable(p, rows_word_aligned);
+    switch (p.interleave == ilv_sample ? p.components : 1)
+    {
+    case 2:
+        return dispatch_encode_nc<2>(p, tiled, grid, block, stream, jobs, slot_bytes);
+    case 3:
+        return dispatch_encode_nc<3>(p, tiled, grid, block, stream, jobs, slot_bytes);
+    case 4:
+        return dispatch_encode_nc<4>(p, tiled, grid, block, stream, jobs, slot_bytes);
+    default:
+        return dispatch_encode_nc<1>(p, tiled, grid, block, stream, jobs, slot_bytes);
+    }
+}
+
+cudaError_t dispatch_decode_fast(const CodecParams& p, bool rows_word_aligned, dim3 grid, dim3 block, cudaStream_t stream,
+                                 const ScanJob* jobs)
+{
+    const bool tiled = rows_tileable(p, rows_word_aligned);
+    switch (p.interleave == ilv_sample ? p.components : 1)
+    {
+    case 2:
+        return dispatch_decode_nc<2>(p, tiled, grid, block, stream, jobs);
+    case 3:
+        return dispatch_decode_nc<3>(p, tiled, grid, block, stream, jobs);
+    case 4:
+        return dispatch_decode_nc<4>(p, tiled, grid, block, stream, jobs);
+    default:
+        return dispatch_decode_nc<1>(p, tiled, grid, block, stream, jobs);
+    }
+}
+
 } // namespace
 
 uint64_t kernel_launch_count() noexcept
@@ -603,7 +728,8 @@ uint64_t kernel_launch_count() noexcept
 
 size_t marker_blocks_for(size_t stream_bytes) noexcept
 {
-    return (stream_bytes + marker_bytes_per_block - 1) / marker_bytes_per_block;
+    // + 15: the chunk grid starts at the 16-byte boundary at or below the first stream byte
+    return (stream_bytes + 15 + marker_bytes_per_block - 1) / marker_bytes_per_block;
 }
 
 #define JLS_TRY(expr)                                                                                                  \
@@ -625,55 +751,7 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
     {
         const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
         const dim3 block(fast_block_threads);
-        const bool wide = p.sample_bytes == 2;
-#define JLS_LAUNCH_ENCODE(NC, LL, LINE)                                                                                \
-    JLS_TRY(wide ? launch(k_encode_fast<NC, LL, uint16_t, LINE>, grid, block, stream, p, device_jobs, slot_bytes)      \
-                 : launch(k_encode_fast<NC, LL, uint8_t, LINE>, grid, block, stream, p, device_jobs, slot_bytes))
-#define JLS_LAUNCH_ENCODE_TILED(NC, LL)                                                                                \
-    JLS_TRY(wide ? launch(k_encode_tiled<NC, LL, uint16_t>, grid, block, stream, p, device_jobs, slot_bytes)           \
-                 : launch(k_encode_tiled<NC, LL, uint8_t>, grid, block, stream, p, device_jobs, slot_bytes))
-        const bool tiled = rows_word_aligned && p.interleave != ilv_line &&
-                           (static_cast<size_t>(p.width) * (p.interleave == ilv_sample ? 3U : 1U) * p.sample_bytes) % 4U == 0;
-        if (tiled)
-        {
-            if (p.interleave == ilv_sample)
-            {
-                if (lossless)
-                    JLS_LAUNCH_ENCODE_TILED(3, true);
-                else
-                    JLS_LAUNCH_ENCODE_TILED(3, false);
-            }
-            else
-            {
-                if (lossless)
-                    JLS_LAUNCH_ENCODE_TILED(1, true);
-                else
-                    JLS_LAUNCH_ENCODE_TILED(1, false);
-            }
-        }
-        else if (p.interleave == ilv_sample)
-        {
-            if (lossless)
-                JLS_LAUNCH_ENCODE(3, true, false);
-            else
-                JLS_LAUNCH_ENCODE(3, false, false);
-        }
-        else if (p.interleave == ilv_line)
-        {
-            if (lossless)
-                JLS_LAUNCH_ENCODE(1, true, true);
-            else
-                JLS_LAUNCH_ENCODE(1, false, true);
-        }
-        else
-        {
-            if (lossless)
-                JLS_LAUNCH_ENCODE(1, true, false);
-            else
-                JLS_LAUNCH_ENCODE(1, false, false);
-        }
-#undef JLS_LAUNCH_ENCODE
-#undef JLS_LAUNCH_ENCODE_TILED
+        JLS_TRY(dispatch_encode_fast(p, rows_word_aligned, grid, block, stream, device_jobs, slot_bytes));
     }
     else
     {
@@ -713,55 +791,7 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
     {
         const dim3 grid((p.interval_count + fast_block_threads - 1) / fast_block_threads, job_count);
         const dim3 block(fast_block_threads);
-        const bool wide = p.sample_bytes == 2;
-#define JLS_LAUNCH_DECODE(NC, LL, LINE)                                                                                \
-    JLS_TRY(wide ? launch(k_decode_fast<NC, LL, uint16_t, LINE>, grid, block, stream, p, device_jobs)                  \
-                 : launch(k_decode_fast<NC, LL, uint8_t, LINE>, grid, block, stream, p, device_jobs))
-#define JLS_LAUNCH_DECODE_TILED(NC, LL)                                                                                \
-    JLS_TRY(wide ? launch(k_decode_tiled<NC, LL, uint16_t>, grid, block, stream, p, device_jobs)                       \
-                 : launch(k_decode_tiled<NC, LL, uint8_t>, grid, block, stream, p, device_jobs))
-        const bool tiled = rows_word_aligned && p.interleave != ilv_line &&
-                           (static_cast<size_t>(p.width) * (p.interleave == ilv_sample ? 3U : 1U) * p.sample_bytes) % 4U == 0;
-        if (tiled)
-        {
-            if (p.interleave == ilv_sample)
-            {
-                if (lossless)
-                    JLS_LAUNCH_DECODE_TILED(3, true);
-                else
-                    JLS_LAUNCH_DECODE_TILED(3, false);
-            }
-            else
-            {
-                if (lossless)
-                    JLS_LAUNCH_DECODE_TILED(1, true);
-                else
-                    JLS_LAUNCH_DECODE_TILED(1, false);
-            }
-        }
-        else if (p.interleave == ilv_sample)
-        {
-            if (lossless)
-                JLS_LAUNCH_DECODE(3, true, false);
-            else
-                JLS_LAUNCH_DECODE(3, false, false);
-        }
-        else if (p.interleave == ilv_line)
-        {
-            if (lossless)
-                JLS_LAUNCH_DECODE(1, true, true);
-            else
-                JLS_LAUNCH_DECODE(1, false, true);
-        }
-        else
-        {
-            if (lossless)
-                JLS_LAUNCH_DECODE(1, true, false);
-            else
-                JLS_LAUNCH_DECODE(1, false, false);
-        }
-#undef JLS_LAUNCH_DECODE
-#undef JLS_LAUNCH_DECODE_TILED
+        JLS_TRY(dispatch_decode_fast(p, rows_word_aligned, grid, block, stream, device_jobs));
     }
     else
     {

@@ -53,7 +53,11 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
 #define HOSTEMU_ENCODE(NC, LL, LINE)                                                                                       \
     (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1, slot_bytes)             \
                          : encode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1, slot_bytes))
-            if (p.interleave == ilv_sample)
+            if (p.interleave == ilv_sample && p.components == 2)
+                r = lossless ? HOSTEMU_ENCODE(2, true, false) : HOSTEMU_ENCODE(2, false, false);
+            else if (p.interleave == ilv_sample && p.components == 4)
+                r = lossless ? HOSTEMU_ENCODE(4, true, false) : HOSTEMU_ENCODE(4, false, false);
+            else if (p.interleave == ilv_sample)
                 r = lossless ? HOSTEMU_ENCODE(3, true, false) : HOSTEMU_ENCODE(3, false, false);
             else if (p.interleave == ilv_line)
                 r = lossless ? HOSTEMU_ENCODE(1, true, true) : HOSTEMU_ENCODE(1, false, true);
@@ -142,7 +146,11 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
 #define HOSTEMU_DECODE(NC, LL, LINE)                                                                                       \
     (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1)                         \
                          : decode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1))
-            if (p.interleave == ilv_sample)
+            if (p.interleave == ilv_sample && p.components == 2)
+                r = lossless ? HOSTEMU_DECODE(2, true, false) : HOSTEMU_DECODE(2, false, false);
+            else if (p.interleave == ilv_sample && p.components == 4)
+                r = lossless ? HOSTEMU_DECODE(4, true, false) : HOSTEMU_DECODE(4, false, false);
+            else if (p.interleave == ilv_sample)
                 r = lossless ? HOSTEMU_DECODE(3, true, false) : HOSTEMU_DECODE(3, false, false);
             else if (p.interleave == ilv_line)
                 r = lossless ? HOSTEMU_DECODE(1, true, true) : HOSTEMU_DECODE(1, false, true);
