@@ -425,8 +425,7 @@ def run_gpu_arm(args):
                 "traffic": traffic.get(f"{name}:{args.workload}:{F}"), "ms_per_launch": ms, "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": algorithmic}
 
-    fast = "k_encode_fast" if True else ""
-    roofs = {"encode": roof("k_encode_fast", t_enc), "decode": roof("k_decode_fast", t_dec)}
+    roofs = {"encode": roof("k_encode_tiled", t_enc), "decode": roof("k_decode_tiled", t_dec)}
     dominant = roofs["encode"] if t_enc >= t_dec else roofs["decode"]
 
     cpu_baseline = None

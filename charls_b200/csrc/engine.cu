@@ -247,6 +247,8 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
                                    cudaMemcpyHostToDevice, stream_));
 
     const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
+    if (slot_bytes >= (size_t{1} << 32))
+        return 7; // parameter_value_not_supported: one restart interval must stay below 4 GiB of entropy-coded data
     const size_t worst_total = static_cast<size_t>(p.interval_count) * (slot_bytes + 2);
     const size_t device_capacity = capacity < worst_total ? capacity : worst_total;
     JLS_CHECK(ensure(stream_buffer_, device_capacity + 64));
@@ -340,6 +342,8 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     cudaStream_t stream = user_stream ? user_stream : stream_;
     const uint64_t launches_before = kernel_launch_count();
     const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
+    if (slot_bytes >= (size_t{1} << 32))
+        return 7; // parameter_value_not_supported, see encode_scan_from_host
 
     JLS_CHECK(ensure(header_, header_size + 16));
     JLS_CHECK(ensure(host_prefixes_, header_size + 16, true));

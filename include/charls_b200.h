@@ -163,143 +163,143 @@ typedef struct charls_jpegls_decoder charls_jpegls_decoder;
 /* Part 1a: encoder (reference include/charls/charls_jpegls_encoder.h)                                                 */
 /* ------------------------------------------------------------------------------------------------------------------ */
 
-/* charls_jpegls_encoder.h:24-33 -- returns NULL when out of memory; destroy(NULL) is a no-op */
+/* charls_jpegls_encoder.h:24-25 -- returns NULL when out of memory; destroy(NULL) is a no-op */
 CHARLS_B200_API charls_jpegls_encoder* charls_jpegls_encoder_create(void) CHARLS_B200_NOEXCEPT;
 CHARLS_B200_API void charls_jpegls_encoder_destroy(const charls_jpegls_encoder* encoder) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:35-44 */
+/* charls_jpegls_encoder.h:41-43 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_frame_info(charls_jpegls_encoder* encoder,
                                                                         const charls_frame_info* frame_info) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:46-54 */
+/* charls_jpegls_encoder.h:51-52 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_near_lossless(charls_jpegls_encoder* encoder,
                                                                            int32_t near_lossless) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:56-66 */
+/* charls_jpegls_encoder.h:60-62 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_encoding_options(charls_jpegls_encoder* encoder,
                                                                               charls_encoding_options encoding_options) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:68-78 */
+/* charls_jpegls_encoder.h:71-73 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_interleave_mode(charls_jpegls_encoder* encoder,
                                                                              charls_interleave_mode interleave_mode) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:80-90 */
+/* charls_jpegls_encoder.h:84-87 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_preset_coding_parameters(
     charls_jpegls_encoder* encoder, const charls_jpegls_pc_parameters* preset_coding_parameters) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:92-101 */
+/* charls_jpegls_encoder.h:98-100 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_color_transformation(
     charls_jpegls_encoder* encoder, charls_color_transformation color_transformation) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:103-115 */
+/* charls_jpegls_encoder.h:109-111 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_mapping_table_id(charls_jpegls_encoder* encoder,
                                                                               int32_t component_index, int32_t table_id) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:117-125.  Reference: raw + raw/16 + 1024 + 34 (src/charls_jpegls_encoder.cpp:104-114);
+/* charls_jpegls_encoder.h:122-124.  Reference: raw + raw/16 + 1024 + 34 (src/charls_jpegls_encoder.cpp:104-114);
    this library adds the restart-marker overhead of the configured restart interval. */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_get_estimated_destination_size(const charls_jpegls_encoder* encoder,
                                                                                         size_t* size_in_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:127-139 -- the buffer is borrowed until the encoder is destroyed or rewound */
+/* charls_jpegls_encoder.h:134-138 -- the buffer is borrowed until the encoder is destroyed or rewound */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_set_destination_buffer(charls_jpegls_encoder* encoder,
                                                                                 void* destination_buffer,
                                                                                 size_t destination_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:141-156 */
+/* charls_jpegls_encoder.h:151-156 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_standard_spiff_header(
     charls_jpegls_encoder* encoder, charls_spiff_color_space color_space, charls_spiff_resolution_units resolution_units,
     uint32_t vertical_resolution, uint32_t horizontal_resolution) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:158-168 */
+/* charls_jpegls_encoder.h:165-167 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_spiff_header(charls_jpegls_encoder* encoder,
                                                                             const charls_spiff_header* spiff_header) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:170-184 */
+/* charls_jpegls_encoder.h:180-184 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_spiff_entry(charls_jpegls_encoder* encoder, uint32_t entry_tag,
                                                                            const void* entry_data,
                                                                            size_t entry_data_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:186-196 */
+/* charls_jpegls_encoder.h:196-197 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_spiff_end_of_directory_entry(charls_jpegls_encoder* encoder) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:198-211 */
+/* charls_jpegls_encoder.h:209-213 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_comment(charls_jpegls_encoder* encoder, const void* comment,
                                                                        size_t comment_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:213-228 */
+/* charls_jpegls_encoder.h:226-230 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_application_data(charls_jpegls_encoder* encoder,
                                                                                 int32_t application_data_id,
                                                                                 const void* application_data,
                                                                                 size_t application_data_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:230-248 */
+/* charls_jpegls_encoder.h:245-249 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_write_mapping_table(charls_jpegls_encoder* encoder, int32_t table_id,
                                                                              int32_t entry_size, const void* table_data,
                                                                              size_t table_data_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:250-266 -- HOT ENTRY POINT.  source_buffer is HOST memory (pinned memory is copied by DMA);
+/* charls_jpegls_encoder.h:262-266 -- HOT ENTRY POINT.  source_buffer is HOST memory (pinned memory is copied by DMA);
    stride in bytes, 0 = tightly packed. Replaces scan_encoder::encode_scan (src/scan_encoder_impl.hpp:42-49). */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_encode_from_buffer(charls_jpegls_encoder* encoder,
                                                                             const void* source_buffer,
                                                                             size_t source_size_bytes, uint32_t stride) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:268-287 */
+/* charls_jpegls_encoder.h:282-287 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_encode_components_from_buffer(
     charls_jpegls_encoder* encoder, const void* source_buffer, size_t source_size_bytes, int32_t source_component_count,
     uint32_t stride) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:289-296 */
+/* charls_jpegls_encoder.h:296-297 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_create_abbreviated_format(charls_jpegls_encoder* encoder) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:298-306 */
+/* charls_jpegls_encoder.h:305-307 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_get_bytes_written(const charls_jpegls_encoder* encoder,
                                                                            size_t* bytes_written) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_encoder.h:308-316 */
+/* charls_jpegls_encoder.h:315-316 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_encoder_rewind(charls_jpegls_encoder* encoder) CHARLS_B200_NOEXCEPT;
 
 /* ------------------------------------------------------------------------------------------------------------------ */
 /* Part 1b: decoder (reference include/charls/charls_jpegls_decoder.h)                                                 */
 /* ------------------------------------------------------------------------------------------------------------------ */
 
-/* charls_jpegls_decoder.h:24-33 */
+/* charls_jpegls_decoder.h:24-25 */
 CHARLS_B200_API charls_jpegls_decoder* charls_jpegls_decoder_create(void) CHARLS_B200_NOEXCEPT;
 CHARLS_B200_API void charls_jpegls_decoder_destroy(const charls_jpegls_decoder* decoder) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:35-48 -- the buffer is borrowed until the decoder is destroyed */
+/* charls_jpegls_decoder.h:43-47 -- the buffer is borrowed until the decoder is destroyed */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_set_source_buffer(charls_jpegls_decoder* decoder,
                                                                            const void* source_buffer,
                                                                            size_t source_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:50-63 */
+/* charls_jpegls_decoder.h:58-61 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_read_spiff_header(charls_jpegls_decoder* decoder,
                                                                            charls_spiff_header* spiff_header,
                                                                            int32_t* header_found) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:65-73 */
+/* charls_jpegls_decoder.h:68-69 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_read_header(charls_jpegls_decoder* decoder) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:75-85 */
+/* charls_jpegls_decoder.h:80-82 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_get_frame_info(const charls_jpegls_decoder* decoder,
                                                                         charls_frame_info* frame_info) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:87-99 */
+/* charls_jpegls_decoder.h:94-96 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_get_near_lossless(const charls_jpegls_decoder* decoder,
                                                                            int32_t component_index, int32_t* near_lossless) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:101-113 */
+/* charls_jpegls_decoder.h:108-110 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_get_interleave_mode(const charls_jpegls_decoder* decoder,
                                                                              int32_t component_index,
                                                                              charls_interleave_mode* interleave_mode) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:115-127 */
+/* charls_jpegls_decoder.h:122-125 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_get_preset_coding_parameters(
     const charls_jpegls_decoder* decoder, int32_t reserved, charls_jpegls_pc_parameters* preset_coding_parameters) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:129-139 */
+/* charls_jpegls_decoder.h:136-138 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_get_color_transformation(
     const charls_jpegls_decoder* decoder, charls_color_transformation* color_transformation) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:141-153 */
+/* charls_jpegls_decoder.h:150-152 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_get_destination_size(const charls_jpegls_decoder* decoder, uint32_t stride,
                                                                               size_t* destination_size_bytes) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:155-172 -- HOT ENTRY POINT.  destination_buffer is HOST memory.
+/* charls_jpegls_decoder.h:168-172 -- HOT ENTRY POINT.  destination_buffer is HOST memory.
    Replaces scan_decoder::decode_scan (src/scan_decoder_impl.hpp:40-56). */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_decode_to_buffer(charls_jpegls_decoder* decoder, void* destination_buffer,
                                                                           size_t destination_size_bytes, uint32_t stride) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:174-188 */
+/* charls_jpegls_decoder.h:185-187 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_at_comment(charls_jpegls_decoder* decoder, charls_at_comment_handler handler,
                                                                     void* user_context) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:190-204 */
+/* charls_jpegls_decoder.h:200-202 */
 CHARLS_B200_API charls_jpegls_errc charls_jpegls_decoder_at_application_data(charls_jpegls_decoder* decoder,
                                                                              charls_at_application_data_handler handler,
                                                                              void* user_context) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:206-217 */
+/* charls_jpegls_decoder.h:214-216 */
 CHARLS_B200_API charls_jpegls_errc charls_decoder_get_compressed_data_format(
     const charls_jpegls_decoder* decoder, charls_compressed_data_format* compressed_data_format) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:219-232 */
+/* charls_jpegls_decoder.h:228-230 */
 CHARLS_B200_API charls_jpegls_errc charls_decoder_get_mapping_table_id(const charls_jpegls_decoder* decoder, int32_t component_index,
                                                                        int32_t* table_id) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:234-247 */
+/* charls_jpegls_decoder.h:243-245 */
 CHARLS_B200_API charls_jpegls_errc charls_decoder_find_mapping_table_index(const charls_jpegls_decoder* decoder,
                                                                            int32_t mapping_table_id, int32_t* index) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:249-259 */
+/* charls_jpegls_decoder.h:256-258 */
 CHARLS_B200_API charls_jpegls_errc charls_decoder_get_mapping_table_count(const charls_jpegls_decoder* decoder, int32_t* count) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:261-274 */
+/* charls_jpegls_decoder.h:272-274 */
 CHARLS_B200_API charls_jpegls_errc charls_decoder_get_mapping_table_info(const charls_jpegls_decoder* decoder,
                                                                          int32_t mapping_table_index,
                                                                          charls_mapping_table_info* mapping_table_info) CHARLS_B200_NOEXCEPT;
-/* charls_jpegls_decoder.h:276-293 */
+/* charls_jpegls_decoder.h:289-293 */
 CHARLS_B200_API charls_jpegls_errc charls_decoder_get_mapping_table_data(const charls_jpegls_decoder* decoder,
                                                                          int32_t mapping_table_index, void* mapping_table_data,
                                                                          size_t mapping_table_size_bytes) CHARLS_B200_NOEXCEPT;
