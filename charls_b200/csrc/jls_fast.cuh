@@ -32,7 +32,13 @@ struct HotParams
 {
     int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init;
     uint32_t dq_magic;
+    // Optional table |Q(-Ra)| for Ra in [0, context_lut_last]; larger Ra use the last entry (they are >= T3).  The tile
+    // kernels keep it in shared memory: one LDS replaces three compares, a select and the adds on the busy ALU pipe.
+    const uint8_t* context_lut;
+    int32_t context_lut_last;
 };
+
+constexpr int32_t context_lut_capacity = 1024; // the table covers T3 <= 1023 (defaults: 21 / 85 / 276 for 8 / 12 / 16 bit)
 
 JLS_HD HotParams make_hot_params(const CodecParams& p)
 {
@@ -52,6 +58,8 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.range_dq = p.range_dq;
     h.a_init = p.a_init;
     h.dq_magic = p.dq_magic;
+    h.context_lut = nullptr;
+    h.context_lut_last = 0;
 #if defined(__CUDA_ARCH__)
     // Keep the hot ones in registers: a value that went through a shuffle is opaque to ptxas, which otherwise re-reads
     // the constant bank (LDC/LDCU) for every use inside the pixel loop -- 5 to 9 issue slots per pixel (profiles/).
@@ -127,6 +135,12 @@ JLS_HD void fast_update_context(const HotParams& h, RegularContext& c, int32_t e
     c.c = low ? c_low : (high ? c_high : c.c);
 }
 
+// Fills entry `index` of the context table (callers loop / stride over [0, last]).
+JLS_HD uint8_t context_lut_entry(const CodecParams& p, int32_t ra_value)
+{
+    return static_cast<uint8_t>((ra_value >= p.t3) + (ra_value >= p.t2) + (ra_value >= p.t1) + (ra_value > p.near));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Bit writer for a slot that is large enough by construction (worst_case_interval_bytes): no capacity checks.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -171,28 +185,47 @@ struct FastWriter
         prev_ff = (b == 0xFFU) ? 1U : 0U;
     }
 
-    // value < 2^count, count in [0, 32]; nbits < 32 on entry and on exit
+    // Moves one 32-bit word (four stuffed bytes when a 0xFF is around) from the accumulator to the slot; nbits >= 32.
+    JLS_HD void flush_word()
+    {
+        const uint32_t w = static_cast<uint32_t>(acc >> (nbits - 32));
+        if (JLS_LIKELY((prev_ff | has_ff_byte(w)) == 0))
+        {
+            *wp++ = bswap32(funnel_r(w, pend, pend_shift));
+            pend = w;
+            nbits -= 32;
+        }
+        else
+        {
+            do
+            {
+                emit_one_stuffed_byte();
+            } while (nbits >= 32);
+        }
+    }
+
+    // value < 2^count, count in [0, 32].  The accumulator holds up to 64 bits; it is drained at a fixed cadence by
+    // drain() (all lanes of a warp at the same pixel), so the branch below is taken only after unusually long codes.
+    // A flush that any one lane needs costs the whole warp its ~15 instructions: at ~4 bits per pixel some lane needed
+    // one at almost every pixel (profiles/r1_notes.md), a drain every 4 pixels costs a quarter of that.
     JLS_HD void put(uint32_t value, int32_t count)
     {
+        if (JLS_UNLIKELY(nbits + count > 64))
+        {
+            do
+            {
+                flush_word();
+            } while (nbits >= 32);
+        }
         acc = (acc << count) | value;
         nbits += count;
-        if (nbits >= 32)
-        {
-            const uint32_t w = static_cast<uint32_t>(acc >> (nbits - 32));
-            if (JLS_LIKELY((prev_ff | has_ff_byte(w)) == 0))
-            {
-                *wp++ = bswap32(funnel_r(w, pend, pend_shift));
-                pend = w;
-                nbits -= 32;
-            }
-            else
-            {
-                do
-                {
-                    emit_one_stuffed_byte();
-                } while (nbits >= 32);
-            }
-        }
+    }
+
+    // brings nbits below 32
+    JLS_HD void drain()
+    {
+        while (nbits >= 32)
+            flush_word();
     }
 
     // limited-length Golomb code (T.87 A.5.3; reference src/scan_encoder_core.hpp:69-103)
@@ -439,7 +472,7 @@ JLS_HD int32_t fast_decode_run_length(FastReader& br, int32_t& run_index, int32_
 // ---------------------------------------------------------------------------------------------------------------------
 // Per-line state shared by encoder and decoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC>
+template<int NC, bool USE_LUT>
 struct FastLineState
 {
     RegularContext* contexts; // this thread's context q lives at contexts[q * context_stride]
@@ -485,9 +518,16 @@ struct FastLineState
     }
 
     // |Q(-Ra)|: di = -Ra <= -T3 -> 4, <= -T2 -> 3, <= -T1 -> 2, < -NEAR -> 1, else 0 (jpegls_algorithm.hpp:173-194)
-    static JLS_HD int32_t context_index(const HotParams& h, int32_t ra_value)
+    static JLS_HD int32_t context_index_compare(const HotParams& h, int32_t ra_value)
     {
         return (ra_value >= h.t3) + (ra_value >= h.t2) + (ra_value >= h.t1) + (ra_value > h.near);
+    }
+
+    static JLS_HD int32_t context_index(const HotParams& h, int32_t ra_value)
+    {
+        if (USE_LUT)
+            return h.context_lut[imin(ra_value, h.context_lut_last)];
+        return context_index_compare(h, ra_value);
     }
 
     JLS_HD bool in_run_mode(const HotParams& h) const
@@ -505,8 +545,8 @@ struct FastLineState
 // ---------------------------------------------------------------------------------------------------------------------
 // Encoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS>
-struct FastLineEncoder : FastLineState<NC>
+template<int NC, bool LOSSLESS, bool USE_LUT = false>
+struct FastLineEncoder : FastLineState<NC, USE_LUT>
 {
     FastWriter bw;
     int32_t run_count;
@@ -520,22 +560,24 @@ struct FastLineEncoder : FastLineState<NC>
 
     JLS_HD void begin_line()
     {
-        FastLineState<NC>::begin_line();
+        FastLineState<NC, USE_LUT>::begin_line();
         run_count = 0;
     }
 
     // regular mode for one sample (reference src/scan_encoder_core.hpp:40-55); prediction = Ra, sign < 0 unless q == 0
     JLS_HD int32_t regular(const HotParams& h, int32_t x, int32_t ra_value)
     {
-        const int32_t q = FastLineState<NC>::context_index(h, ra_value);
+        const int32_t q = FastLineState<NC, USE_LUT>::context_index(h, ra_value);
         this->select_context(q);
         RegularContext& c = this->cached;
         const int32_t k = golomb_parameter(c.a, c.n);
         const bool negative = NC == 1 || q != 0; // a scalar line reaches regular mode only with q != 0
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
         const int32_t e = fast_error_value<LOSSLESS>(h, negative ? pv - x : x - pv);
-        const int32_t correction = (LOSSLESS ? k : (k | h.near)) == 0 ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
-        bw.put_golomb(h, k, map_error_value(correction ^ e), h.escape);
+        // map(correction ^ e) with correction in {0, -1} equals map(e) ^ (correction & 1): the reference's XOR trick
+        // (src/scan_encoder_core.hpp:48-53, src/regular_mode_context.hpp:36-42) costs one conditional bit flip here
+        const bool flip = (LOSSLESS ? k : (k | h.near)) == 0 && 2 * c.b + c.n < 1;
+        bw.put_golomb(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
         fast_update_context<LOSSLESS>(h, c, e);
         return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
     }
@@ -595,6 +637,9 @@ struct FastLineEncoder : FastLineState<NC>
             this->ra[c] = regular(h, x[c], this->ra[c]);
     }
 
+    // called by the pixel loop every few pixels, by all lanes at the same time (see FastWriter::put)
+    JLS_HD void drain() { bw.drain(); }
+
     // end of a line: a run that reaches the end of the line (reference src/scan_encoder.hpp:62-68)
     JLS_HD void end_line()
     {
@@ -611,8 +656,8 @@ struct FastLineEncoder : FastLineState<NC>
 // ---------------------------------------------------------------------------------------------------------------------
 // Decoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS>
-struct FastLineDecoder : FastLineState<NC>
+template<int NC, bool LOSSLESS, bool USE_LUT = false>
+struct FastLineDecoder : FastLineState<NC, USE_LUT>
 {
     FastReader br;
     int32_t run_left;    // pixels of the current run still to be output
@@ -630,7 +675,7 @@ struct FastLineDecoder : FastLineState<NC>
 
     JLS_HD void begin_line()
     {
-        FastLineState<NC>::begin_line();
+        FastLineState<NC, USE_LUT>::begin_line();
         run_left = 0;
         need_interrupt = false;
     }
@@ -638,7 +683,7 @@ struct FastLineDecoder : FastLineState<NC>
     // reference src/scan_decoder_core.hpp:38-69
     JLS_HD int32_t regular(const HotParams& h, int32_t ra_value)
     {
-        const int32_t q = FastLineState<NC>::context_index(h, ra_value);
+        const int32_t q = FastLineState<NC, USE_LUT>::context_index(h, ra_value);
         this->select_context(q);
         RegularContext& c = this->cached;
         const bool negative = NC == 1 || q != 0;
@@ -649,9 +694,8 @@ struct FastLineDecoder : FastLineState<NC>
             br.bad = 1;
             k = 15;
         }
-        int32_t e = unmap_error_value(br.get_golomb(h, k, h.escape));
-        if (k == 0)
-            e ^= (LOSSLESS || h.near == 0) ? bit_wise_sign(2 * c.b + c.n - 1) : 0;
+        const bool flip = k == 0 && (LOSSLESS || h.near == 0) && 2 * c.b + c.n < 1; // see the encoder
+        const int32_t e = unmap_error_value(br.get_golomb(h, k, h.escape) ^ (flip ? 1 : 0));
         fast_update_context<LOSSLESS>(h, c, e);
         // the reference's sanity checks (src/scan_decoder_core.hpp:57-58, src/regular_mode_context.hpp:52-54)
         // a >= 0; one test covers a >= 2^24, |b| >= 2^24 and |e| > 65535

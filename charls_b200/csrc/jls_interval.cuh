@@ -83,12 +83,16 @@ JLS_HD void fast_store_pixel(const CodecParams& p, S* line, int32_t x, const int
 }
 
 // LINE_ILV: the interval holds one line of each of p.components components (line interleave); NC must be 1 then.
-template<int NC, bool LOSSLESS, typename S, bool LINE_ILV>
+// USE_LUT: context_lut holds context_lut_entry(p, 0 .. min(T3, capacity - 1)).
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, bool USE_LUT = false>
 JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
-                                           RegularContext* contexts, int32_t context_stride, size_t slot_bytes)
+                                           RegularContext* contexts, int32_t context_stride, size_t slot_bytes,
+                                           const uint8_t* context_lut = nullptr)
 {
-    const HotParams h = make_hot_params(p);
-    FastLineEncoder<NC, LOSSLESS> enc;
+    HotParams h = make_hot_params(p);
+    h.context_lut = context_lut;
+    h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
+    FastLineEncoder<NC, LOSSLESS, USE_LUT> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(interval) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts, context_stride, slot);
@@ -106,6 +110,8 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
             enc.begin_line();
             for (int32_t x = 0; x < width; ++x)
             {
+                if ((x & 3) == 3)
+                    enc.drain();
                 const int32_t v[1] = {load_line_component(p, bytes, x, c)};
                 enc.pixel(h, v);
             }
@@ -116,6 +122,8 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
     {
         for (int32_t x = 0; x < width; ++x)
         {
+            if ((x & 3) == 3)
+                enc.drain();
             int32_t v[NC];
             fast_load_pixel<NC, S>(p, h, line, x, v);
             enc.pixel(h, v);
@@ -151,9 +159,10 @@ JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool 
     return br.unread_bytes() > 7 ? err_restart_marker_not_found : err_none;
 }
 
-template<int NC, bool LOSSLESS, typename S, bool LINE_ILV>
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, bool USE_LUT = false>
 JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
-                                           RegularContext* contexts, int32_t context_stride)
+                                           RegularContext* contexts, int32_t context_stride,
+                                           const uint8_t* context_lut = nullptr)
 {
     IntervalResult result = {err_none, 0};
     // interval_offset holds 2 entries per interval: [2i] = first byte, [2i+1] = end (first 0xFF of the closing marker)
@@ -167,8 +176,10 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
     if (begin > end)
         return result;
 
-    const HotParams h = make_hot_params(p);
-    FastLineDecoder<NC, LOSSLESS> dec;
+    HotParams h = make_hot_params(p);
+    h.context_lut = context_lut;
+    h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
+    FastLineDecoder<NC, LOSSLESS, USE_LUT> dec;
     dec.begin(h, contexts, context_stride, job.stream_in + begin, job.stream_in + end);
     S* line = reinterpret_cast<S*>(job.pixels_out + static_cast<size_t>(interval) * job.stride);
     assume_global(line);

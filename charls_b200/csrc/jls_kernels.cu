@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int warps = fast_block_threads / 32;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][2][32 * SW];
+    __shared__ uint8_t context_lut[context_lut_capacity];
+
+    const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
+    for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
+        context_lut[i] = context_lut_entry(p, i);
+    __syncthreads();
 
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,8 +102,10 @@ __global__ void __launch_bounds__(fast_block_threads)
     const uint32_t interval = first_line + lane;
     const bool active = interval < p.interval_count;
 
-    const HotParams h = make_hot_params(p);
-    FastLineEncoder<NC, LOSSLESS> enc;
+    HotParams h = make_hot_params(p);
+    h.context_lut = context_lut;
+    h.context_lut_last = lut_last;
+    FastLineEncoder<NC, LOSSLESS, true> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts + threadIdx.x, fast_block_threads, slot);
@@ -129,8 +137,11 @@ __global__ void __launch_bounds__(fast_block_threads)
         {
             const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
             const S* const tile_end = sample + min(pixels_per_tile, width - t * pixels_per_tile) * NC;
+            uint32_t cadence = 0;
             for (; sample != tile_end; sample += NC)
             {
+                if ((++cadence & 3U) == 0)
+                    enc.drain(); // uniform across the warp
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -166,6 +177,12 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int warps = fast_block_threads / 32;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
+    __shared__ uint8_t context_lut[context_lut_capacity];
+
+    const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
+    for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
+        context_lut[i] = context_lut_entry(p, i);
+    __syncthreads();
 
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -189,8 +206,10 @@ __global__ void __launch_bounds__(fast_block_threads)
     }
     const uint32_t row_mask = __ballot_sync(0xFFFFFFFFU, coding);
 
-    const HotParams h = make_hot_params(p);
-    FastLineDecoder<NC, LOSSLESS> dec;
+    HotParams h = make_hot_params(p);
+    h.context_lut = context_lut;
+    h.context_lut_last = lut_last;
+    FastLineDecoder<NC, LOSSLESS, true> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
     dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
@@ -631,7 +650,7 @@ cudaError_t launch(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, Ar
 bool rows_tileable(const CodecParams& p, bool rows_word_aligned)
 {
     const size_t samples_per_pixel = p.interleave == ilv_sample ? static_cast<size_t>(p.components) : 1U;
-    return rows_word_aligned && p.interleave != ilv_line &&
+    return rows_word_aligned && p.interleave != ilv_line && p.t3 < context_lut_capacity &&
            (static_cast<size_t>(p.width) * samples_per_pixel * static_cast<size_t>(p.sample_bytes)) % 4U == 0;
 }
 

@@ -10,6 +10,25 @@
 
 using namespace jls;
 
+namespace {
+
+// The tile kernels look the context index up in a shared-memory table; odd intervals take that variant here so that
+// both it and the compare chain are checked against the oracle in every multi-line test.
+bool use_lut(const CodecParams& p, uint32_t interval)
+{
+    return p.t3 < context_lut_capacity && (interval & 1U) != 0;
+}
+
+std::vector<uint8_t> make_lut(const CodecParams& p)
+{
+    std::vector<uint8_t> lut(context_lut_capacity, 0);
+    for (int32_t i = 0; i <= std::min(p.t3, context_lut_capacity - 1); ++i)
+        lut[static_cast<size_t>(i)] = context_lut_entry(p, i);
+    return lut;
+}
+
+} // namespace
+
 extern "C" {
 
 // returns 0 on success
@@ -43,6 +62,7 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
 
     const bool fast = use_fast_path(p) && !force_general;
     const bool lossless = p.near == 0;
+    const std::vector<uint8_t> lut = make_lut(p);
     RegularContext contexts[5];
     uint64_t first_error = ~0ULL;
     for (uint32_t i = 0; i < p.interval_count; ++i)
@@ -51,8 +71,10 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
         if (fast)
         {
 #define HOSTEMU_ENCODE(NC, LL, LINE)                                                                                       \
-    (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1, slot_bytes)             \
-                         : encode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1, slot_bytes))
+    (use_lut(p, i) ? (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data()) \
+                                          : encode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data()))   \
+                   : (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1, slot_bytes)                   \
+                                          : encode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1, slot_bytes)))
             if (p.interleave == ilv_sample && p.components == 2)
                 r = lossless ? HOSTEMU_ENCODE(2, true, false) : HOSTEMU_ENCODE(2, false, false);
             else if (p.interleave == ilv_sample && p.components == 4)
@@ -133,6 +155,7 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
 
     const bool fast = use_fast_path(p) && !force_general;
     const bool lossless = p.near == 0;
+    const std::vector<uint8_t> lut = make_lut(p);
     RegularContext contexts[5];
     uint64_t first_error = ~0ULL;
     auto report = [&](uint32_t interval, int32_t errc) {
@@ -144,8 +167,10 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
         if (fast)
         {
 #define HOSTEMU_DECODE(NC, LL, LINE)                                                                                       \
-    (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1)                         \
-                         : decode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1))
+    (use_lut(p, i) ? (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, lut.data()) \
+                                          : decode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, lut.data()))   \
+                   : (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1)                   \
+                                          : decode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1)))
             if (p.interleave == ilv_sample && p.components == 2)
                 r = lossless ? HOSTEMU_DECODE(2, true, false) : HOSTEMU_DECODE(2, false, false);
             else if (p.interleave == ilv_sample && p.components == 4)
