@@ -208,17 +208,30 @@ struct FastWriter
     // drain() (all lanes of a warp at the same pixel), so the branch below is taken only after unusually long codes.
     // A flush that any one lane needs costs the whole warp its ~15 instructions: at ~4 bits per pixel some lane needed
     // one at almost every pixel (profiles/r1_notes.md), a drain every 4 pixels costs a quarter of that.
+    // DEFERRED = false flushes as soon as 32 bits are pending (best when most samples produce a word anyway: lossless
+    // 16-bit data at 10+ bits per sample); DEFERRED = true leaves it to drain().
+    template<bool DEFERRED>
     JLS_HD void put(uint32_t value, int32_t count)
     {
-        if (JLS_UNLIKELY(nbits + count > 64))
+        if (DEFERRED)
         {
-            do
+            if (JLS_UNLIKELY(nbits + count > 64))
             {
-                flush_word();
-            } while (nbits >= 32);
+                do
+                {
+                    flush_word();
+                } while (nbits >= 32);
+            }
+            acc = (acc << count) | value;
+            nbits += count;
         }
-        acc = (acc << count) | value;
-        nbits += count;
+        else
+        {
+            acc = (acc << count) | value;
+            nbits += count;
+            if (nbits >= 32)
+                flush_word();
+        }
     }
 
     // brings nbits below 32
@@ -229,27 +242,28 @@ struct FastWriter
     }
 
     // limited-length Golomb code (T.87 A.5.3; reference src/scan_encoder_core.hpp:69-103)
+    template<bool DEFERRED>
     JLS_HD void put_golomb(const HotParams& h, int32_t k, int32_t mapped, int32_t escape)
     {
         const int32_t high = mapped >> k;
         const int32_t length = high + 1 + k;
         if (JLS_LIKELY(high < escape && length <= 32))
         {
-            put((1U << k) | (static_cast<uint32_t>(mapped) & ((1U << k) - 1U)), length);
+            put<DEFERRED>((1U << k) | (static_cast<uint32_t>(mapped) & ((1U << k) - 1U)), length);
             return;
         }
         // long code word (more than 32 bits) or escape code: unary part in at most two pieces, then the binary part
         int32_t zeros = high < escape ? high : escape;
         if (zeros > 31)
         {
-            put(0, 31);
+            put<DEFERRED>(0, 31);
             zeros -= 31;
         }
-        put(1, zeros + 1);
+        put<DEFERRED>(1, zeros + 1);
         if (high < escape)
-            put(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
+            put<DEFERRED>(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
         else
-            put(static_cast<uint32_t>(mapped - 1) & ((1U << h.qbpp) - 1U), h.qbpp);
+            put<DEFERRED>(static_cast<uint32_t>(mapped - 1) & ((1U << h.qbpp) - 1U), h.qbpp);
     }
 
     // reference src/scan_encoder.hpp:103-115: zero-pad to a byte; a final 0xFF is followed by a zero byte
@@ -283,11 +297,12 @@ struct FastWriter
 };
 
 // reference src/scan_encoder.hpp:53-73
+template<bool DEFERRED>
 JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t run_length, bool end_of_line)
 {
     while (run_length >= (1 << run_order(run_index)))
     {
-        bw.put(1, 1);
+        bw.put<DEFERRED>(1, 1);
         run_length -= 1 << run_order(run_index);
         if (run_index < 31)
             ++run_index;
@@ -295,11 +310,11 @@ JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t r
     if (end_of_line)
     {
         if (run_length != 0)
-            bw.put(1, 1);
+            bw.put<DEFERRED>(1, 1);
     }
     else
     {
-        bw.put(static_cast<uint32_t>(run_length), run_order(run_index) + 1);
+        bw.put<DEFERRED>(static_cast<uint32_t>(run_length), run_order(run_index) + 1);
     }
 }
 
@@ -545,7 +560,7 @@ struct FastLineState
 // ---------------------------------------------------------------------------------------------------------------------
 // Encoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS, bool USE_LUT = false>
+template<int NC, bool LOSSLESS, bool USE_LUT = false, bool DEFERRED = true>
 struct FastLineEncoder : FastLineState<NC, USE_LUT>
 {
     FastWriter bw;
@@ -577,7 +592,7 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
         // map(correction ^ e) with correction in {0, -1} equals map(e) ^ (correction & 1): the reference's XOR trick
         // (src/scan_encoder_core.hpp:48-53, src/regular_mode_context.hpp:36-42) costs one conditional bit flip here
         const bool flip = (LOSSLESS ? k : (k | h.near)) == 0 && 2 * c.b + c.n < 1;
-        bw.put_golomb(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
+        bw.template put_golomb<DEFERRED>(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
         fast_update_context<LOSSLESS>(h, c, e);
         return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
     }
@@ -589,7 +604,7 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
         const int32_t k = run_golomb_parameter(c, ri_type);
         const int32_t map = run_compute_map(c, e, k);
         const int32_t e_mapped = 2 * iabs(e) - ri_type - map;
-        bw.put_golomb(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
+        bw.template put_golomb<DEFERRED>(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
         update_run_context(c, e, e_mapped, ri_type, h.reset);
     }
 
@@ -607,7 +622,7 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
                 ++run_count; // reconstructed value is Ra (scan_encoder_impl.hpp:258-265)
                 return;
             }
-            fast_encode_run_length(bw, this->run_index, run_count, false);
+            fast_encode_run_length<DEFERRED>(bw, this->run_index, run_count, false);
             run_count = 0;
 #pragma unroll
             for (int32_t c = 0; c < NC; ++c)
@@ -645,7 +660,7 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
     {
         if (run_count != 0)
         {
-            fast_encode_run_length(bw, this->run_index, run_count, true);
+            fast_encode_run_length<DEFERRED>(bw, this->run_index, run_count, true);
             run_count = 0;
         }
     }

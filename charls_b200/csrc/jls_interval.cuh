@@ -92,7 +92,7 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
     HotParams h = make_hot_params(p);
     h.context_lut = context_lut;
     h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
-    FastLineEncoder<NC, LOSSLESS, USE_LUT> enc;
+    FastLineEncoder<NC, LOSSLESS, USE_LUT, !(LOSSLESS && sizeof(S) == 2)> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(interval) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts, context_stride, slot);

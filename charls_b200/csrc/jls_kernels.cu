@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     HotParams h = make_hot_params(p);
     h.context_lut = context_lut;
     h.context_lut_last = lut_last;
-    FastLineEncoder<NC, LOSSLESS, true> enc;
+    // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
+    FastLineEncoder<NC, LOSSLESS, true, !(LOSSLESS && sizeof(S) == 2)> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts + threadIdx.x, fast_block_threads, slot);
@@ -177,12 +178,6 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int warps = fast_block_threads / 32;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
-    __shared__ uint8_t context_lut[context_lut_capacity];
-
-    const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
-    for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
-        context_lut[i] = context_lut_entry(p, i);
-    __syncthreads();
 
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,10 +201,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     }
     const uint32_t row_mask = __ballot_sync(0xFFFFFFFFU, coding);
 
-    HotParams h = make_hot_params(p);
-    h.context_lut = context_lut;
-    h.context_lut_last = lut_last;
-    FastLineDecoder<NC, LOSSLESS, true> dec;
+    const HotParams h = make_hot_params(p);
+    FastLineDecoder<NC, LOSSLESS, false> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
     dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
