@@ -67,6 +67,16 @@ JLS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift)
 #endif
 }
 
+// high 32 bits of (hi:lo) << shift, shift in [0, 32]
+JLS_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t shift)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(lo, hi, shift);
+#else
+    return shift == 0 ? hi : shift >= 32 ? lo : (hi << shift) | (lo >> (32 - shift));
+#endif
+}
+
 JLS_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
@@ -499,6 +509,7 @@ struct BitReader
         }
     }
 
+    JLS_HD bool residue() const { return cache != 0; } // bits that were not consumed are not all zero
     JLS_HD uint32_t peek(int32_t count) const { return static_cast<uint32_t>(cache >> (64 - count)); } // count 1..32
 
     JLS_HD void skip(int32_t count) // count 0..63

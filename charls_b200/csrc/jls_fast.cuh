@@ -320,24 +320,31 @@ JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t r
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Bit reader over [begin, end) of one interval; bytes past `end` read as zero and are accounted for.
+//
+// The window is 128 bits wide (four registers).  A code word needs at most 32 valid bits, so a window that is topped up
+// to > 96 bits survives several pixels without a refill: the pixel loop calls top_up() every few pixels from all lanes
+// of the warp at the same time, and the refill inside get_golomb()/read() is a rarely taken fall-back.  With a 64-bit
+// window some lane of the warp needed a word at nearly every symbol and the whole warp paid for the refill each time.
 // ---------------------------------------------------------------------------------------------------------------------
 struct FastReader
 {
-    uint64_t cache;       // left aligned
-    int32_t valid;        // valid bits in cache
-    int32_t virtual_bits; // appended bits that lie beyond the end of the interval
-    int32_t remaining;    // real bytes not yet moved into the cache (may go negative)
-    int32_t guard;        // > 0 while the word after `cur` still holds bytes of the interval
+    uint32_t c3, c2, c1, c0; // the window, left aligned: c3 holds the next bits
+    int32_t valid;           // valid bits in the window
+    int32_t virtual_bits;    // appended bits that lie beyond the end of the interval
+    int32_t remaining;       // real bytes not yet moved into the window (may go negative)
+    int32_t guard;           // > 0 while the word after `cur` still holds bytes of the interval
     uint32_t prev_ff;
     uint32_t bad;         // malformed code word seen
     const uint32_t* wptr; // aligned word that holds the next byte to fetch
     uint32_t cur;         // *wptr
-    uint32_t ahead;       // wptr[1], loaded one refill early so that its latency is hidden behind ~8 pixels of work
+    uint32_t ahead;       // wptr[1], loaded one refill early so that its latency is hidden behind several pixels of work
     uint32_t shift;       // 8 * (offset of the next byte inside *wptr)
+
+    static constexpr int32_t full_mark = 96; // a refill appends words while valid <= full_mark
 
     JLS_HD void init(const uint8_t* begin, const uint8_t* end)
     {
-        cache = 0;
+        c3 = c2 = c1 = c0 = 0;
         valid = 0;
         virtual_bits = 0;
         prev_ff = 0;
@@ -356,17 +363,39 @@ struct FastReader
         refill();
     }
 
-    JLS_HD void append_byte(uint32_t b, bool is_virtual)
+    // appends the low `count` bits of `bits` (count in [1, 32], valid + count <= 128)
+    JLS_HD void append(uint32_t bits, int32_t count)
     {
-        const int32_t take = prev_ff ? 7 : 8;
-        cache |= static_cast<uint64_t>(b & (0xFFU >> (8 - take))) << (64 - take - valid);
-        valid += take;
-        if (is_virtual)
-            virtual_bits += take;
-        prev_ff = (b == 0xFFU) ? 1U : 0U;
+        const uint64_t v = static_cast<uint64_t>(bits) << (64 - count); // left aligned in 64 bits
+        if (JLS_LIKELY(valid >= 64))
+        {
+            const uint64_t piece = v >> (valid - 64);
+            c1 |= static_cast<uint32_t>(piece >> 32);
+            c0 |= static_cast<uint32_t>(piece);
+        }
+        else
+        {
+            const uint64_t piece = v >> valid;
+            c3 |= static_cast<uint32_t>(piece >> 32);
+            c2 |= static_cast<uint32_t>(piece);
+            if (valid > 32)
+                c1 |= static_cast<uint32_t>(v >> 32) << (64 - valid); // the part that crosses into the lower half
+        }
+        valid += count;
     }
 
-    JLS_HD void refill_once() // valid <= 32 on entry
+    // drops `count` bits, count in [0, 32]
+    JLS_HD void consume(int32_t count)
+    {
+        const uint32_t n = static_cast<uint32_t>(count);
+        c3 = funnel_l(c2, c3, n);
+        c2 = funnel_l(c1, c2, n);
+        c1 = funnel_l(c0, c1, n);
+        c0 = funnel_l(0U, c0, n);
+        valid -= count;
+    }
+
+    JLS_HD void refill_once() // valid <= full_mark on entry
     {
         const uint32_t w = bswap32(funnel_r(cur, ahead, shift)); // the next four bytes, first one on top
         cur = ahead;
@@ -378,37 +407,55 @@ struct FastReader
         ahead = guard > 0 ? wptr[1] : 0U; // needed only at the next refill
         if (JLS_LIKELY(remaining >= 4 && (prev_ff | has_ff_byte(w)) == 0))
         {
-            cache |= static_cast<uint64_t>(w) << (32 - valid);
-            valid += 32;
+            append(w, 32);
         }
         else
         {
+            // bit stuffing (the byte after 0xFF carries 7 bits) and the zero bytes beyond the end of the interval
+            uint32_t bits = 0;
+            int32_t count = 0;
             for (int32_t i = 0; i < 4; ++i)
             {
                 const bool is_virtual = i >= remaining;
-                append_byte(is_virtual ? 0U : (w >> (24 - 8 * i)) & 0xFFU, is_virtual);
+                const uint32_t b = is_virtual ? 0U : (w >> (24 - 8 * i)) & 0xFFU;
+                const int32_t take = prev_ff ? 7 : 8;
+                bits = (bits << take) | (b & (0xFFU >> (8 - take)));
+                count += take;
+                if (is_virtual)
+                    virtual_bits += take;
+                prev_ff = (b == 0xFFU) ? 1U : 0U;
             }
+            append(bits, count);
         }
         remaining -= 4;
     }
 
-    JLS_HD void refill() // afterwards valid > 32
+    JLS_HD void refill() // afterwards valid > full_mark
     {
-        while (valid <= 32)
+        while (valid <= full_mark)
             refill_once();
+    }
+
+    // the pixel loop's cadence call (all lanes of a warp together)
+    JLS_HD void top_up()
+    {
+        if (valid <= full_mark)
+            refill();
     }
 
     JLS_HD uint32_t read(int32_t count) // count in [1, 31]
     {
-        if (JLS_UNLIKELY(valid < count))
+        if (JLS_UNLIKELY(valid <= 32))
             refill();
-        const uint32_t v = static_cast<uint32_t>(cache >> (64 - count));
-        cache <<= count;
-        valid -= count;
+        const uint32_t v = c3 >> (32 - count);
+        consume(count);
         return v;
     }
 
     JLS_HD bool overrun() const { return valid < virtual_bits; }
+
+    // true when bits that were not consumed are not all zero
+    JLS_HD bool residue() const { return (c3 | c2 | c1 | c0) != 0; }
 
     // whole unread bytes left in the interval after the last decoded symbol
     JLS_HD int32_t unread_bytes() const
@@ -420,17 +467,16 @@ struct FastReader
     // limited-length Golomb code (reference src/scan_decoder.hpp:113-125,203-217); `bad` on a malformed code
     JLS_HD int32_t get_golomb(const HotParams& h, int32_t k, int32_t escape)
     {
-        if (valid <= 32)
+        if (JLS_UNLIKELY(valid <= 32))
             refill();
-        const uint32_t top = static_cast<uint32_t>(cache >> 32);
+        const uint32_t top = c3;
         const int32_t z = clz32(top);
         const int32_t length = z + 1 + k;
         if (JLS_LIKELY(z < escape && length <= 32))
         {
             // the whole code word sits in the top 32 bits (valid > 32)
             const uint32_t remainder = ((top << z) << 1) >> 1 >> (31 - k);
-            cache <<= length;
-            valid -= length;
+            consume(length);
             return (z << k) + static_cast<int32_t>(remainder);
         }
         int32_t zeros = 0;
@@ -438,17 +484,15 @@ struct FastReader
         {
             if (valid <= 32)
                 refill();
-            const int32_t n = clz64(cache);
-            if (n < valid)
+            const int32_t n = clz32(c3); // valid > 32: all of c3 is valid
+            if (n < 32)
             {
                 zeros += n;
-                cache = (cache << n) << 1;
-                valid -= n + 1;
+                consume(n + 1);
                 break;
             }
-            zeros += valid;
-            cache = 0;
-            valid = 0;
+            zeros += 32;
+            consume(32);
             if (overrun()) // ran off the end of the interval inside a unary code (the reference: invalid_data)
             {
                 bad = 1;
@@ -675,24 +719,26 @@ template<int NC, bool LOSSLESS, bool USE_LUT = false>
 struct FastLineDecoder : FastLineState<NC, USE_LUT>
 {
     FastReader br;
-    int32_t run_left;    // pixels of the current run still to be output
-    bool need_interrupt; // a run-interruption pixel follows the current run
+    // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
+    // register and one test on the regular-mode path
+    int32_t pending;
 
     JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, const uint8_t* begin_, const uint8_t* end_)
     {
         this->begin_interval(h, ctx, stride);
         br.init(begin_, end_);
-        run_left = 0;
-        need_interrupt = false;
+        pending = 0;
     }
 
     JLS_HD bool bad() const { return br.bad != 0; }
 
+    // called by the pixel loop every few pixels, by all lanes at the same time (see FastReader)
+    JLS_HD void top_up() { br.top_up(); }
+
     JLS_HD void begin_line()
     {
         FastLineState<NC, USE_LUT>::begin_line();
-        run_left = 0;
-        need_interrupt = false;
+        pending = 0;
     }
 
     // reference src/scan_decoder_core.hpp:38-69
@@ -738,20 +784,18 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
         }
         if (this->run_index > 0)
             --this->run_index;
-        need_interrupt = false;
+        pending = 0;
     }
 
     // Decodes one pixel into this->ra. `remaining` = pixels left in the line including this one.
     JLS_HD void pixel(const HotParams& h, int32_t remaining)
     {
-        if (JLS_UNLIKELY(run_left > 0))
+        if (JLS_UNLIKELY(pending != 0))
         {
-            --run_left;
-            return;
-        }
-        if (JLS_UNLIKELY(need_interrupt))
-        {
-            interruption(h);
+            if (pending > 1)
+                pending -= 2; // a pixel of the run: Ra stays
+            else
+                interruption(h);
             return;
         }
         if (JLS_UNLIKELY(this->in_run_mode(h)))
@@ -762,13 +806,14 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
                 br.bad = 1; // reference scan_decoder_impl.hpp:328-329
                 return;
             }
-            need_interrupt = length != remaining;
+            pending = (length != remaining ? 1 : 0);
             if (length > 0)
             {
-                run_left = length - 1;
+                pending += 2 * (length - 1);
                 return;
             }
-            interruption(h);
+            if (pending != 0)
+                interruption(h);
             return;
         }
 #pragma unroll

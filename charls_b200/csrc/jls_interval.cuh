@@ -153,7 +153,7 @@ JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool 
     if (interval + 1 == p.interval_count)
     {
         // left-over bits must be zero padding and the closing marker must follow directly
-        return (br.cache != 0 || br.unread_bytes() > 0) ? err_invalid_data : err_none;
+        return (br.residue() || br.unread_bytes() > 0) ? err_invalid_data : err_none;
     }
     // the reference looks for RSTm where its 64-bit read cache stopped
     return br.unread_bytes() > 7 ? err_restart_marker_not_found : err_none;
@@ -196,6 +196,8 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
                 dec.begin_line();
                 for (int32_t x = 0; x < width; ++x)
                 {
+                    if ((x & 3) == 0)
+                        dec.top_up();
                     dec.pixel(h, width - x);
                     line[x * nc + c] = static_cast<S>(dec.ra[0]);
                 }
@@ -217,6 +219,8 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
     {
         for (int32_t x = 0; x < width; ++x)
         {
+            if ((x & 3) == 0)
+                dec.top_up();
             dec.pixel(h, width - x);
             fast_store_pixel<NC, S>(p, line, x, dec.ra);
         }

@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
+    // pixels between two top-ups of the 128-bit read window (~4 bits per 8-bit sample on image data)
+    constexpr int refill_cadence = (NC == 1 && sizeof(S) == 1) ? 4 : 2;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
 
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(fast_block_threads)
             S* const tile_end = sample + min(pixels_per_tile, width - x0) * NC;
             for (int32_t left = width - x0; sample != tile_end; sample += NC, --left)
             {
+                if ((left & (refill_cadence - 1)) == 0)
+                    dec.top_up();
                 dec.pixel(h, left);
                 int32_t v[NC];
 #pragma unroll
