@@ -77,6 +77,29 @@ JLS_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t shift)
 #endif
 }
 
+// shifts whose count may reach 32 (the result is then 0): PTX defines that, C++ does not
+JLS_HD uint32_t shl_sat(uint32_t v, uint32_t count)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(count));
+    return r;
+#else
+    return count >= 32 ? 0U : v << count;
+#endif
+}
+
+JLS_HD uint32_t shr_sat(uint32_t v, uint32_t count)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(count));
+    return r;
+#else
+    return count >= 32 ? 0U : v >> count;
+#endif
+}
+
 JLS_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)

@@ -60,21 +60,38 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.dq_magic = p.dq_magic;
     h.context_lut = nullptr;
     h.context_lut_last = 0;
-#if defined(__CUDA_ARCH__)
-    // Keep the hot ones in registers: a value that went through a shuffle is opaque to ptxas, which otherwise re-reads
-    // the constant bank (LDC/LDCU) for every use inside the pixel loop -- 5 to 9 issue slots per pixel (profiles/).
-    const int lane = static_cast<int>(threadIdx.x & 31U);
-    h.t1 = __shfl_sync(0xFFFFFFFFU, h.t1, lane);
-    h.t2 = __shfl_sync(0xFFFFFFFFU, h.t2, lane);
-    h.t3 = __shfl_sync(0xFFFFFFFFU, h.t3, lane);
-    h.near = __shfl_sync(0xFFFFFFFFU, h.near, lane);
-    h.reset = __shfl_sync(0xFFFFFFFFU, h.reset, lane);
-    h.escape = __shfl_sync(0xFFFFFFFFU, h.escape, lane);
-    h.maxval = __shfl_sync(0xFFFFFFFFU, h.maxval, lane);
-    h.bits = __shfl_sync(0xFFFFFFFFU, h.bits, lane);
-#endif
     return h;
 }
+
+#if defined(__CUDACC__)
+// Moves the parameters the pixel loop reads into registers.  Kernel parameters live in the constant bank and ptxas
+// re-reads them (LDC / LDCU, one issue slot each) at every use instead of spending a register: 5 to 9 slots per pixel.
+// It also sees through shuffles and register moves of such warp-uniform values, so they take a round trip through
+// `scratch` (8 words of shared memory owned by the calling warp; all 32 lanes call this).
+__device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volatile int32_t* scratch)
+{
+    if ((threadIdx.x & 31U) == 0)
+    {
+        scratch[0] = h.t1;
+        scratch[1] = h.t2;
+        scratch[2] = h.t3;
+        scratch[3] = h.near;
+        scratch[4] = h.reset;
+        scratch[5] = h.escape;
+        scratch[6] = h.maxval;
+        scratch[7] = h.bits;
+    }
+    __syncwarp();
+    h.t1 = scratch[0];
+    h.t2 = scratch[1];
+    h.t3 = scratch[2];
+    h.near = scratch[3];
+    h.reset = scratch[4];
+    h.escape = scratch[5];
+    h.maxval = scratch[6];
+    h.bits = scratch[7];
+}
+#endif
 
 template<bool LOSSLESS>
 JLS_HD int32_t fast_error_value(const HotParams& h, int32_t e)
@@ -111,12 +128,15 @@ JLS_HD int32_t fast_reconstruct(const HotParams& h, int32_t predicted, int32_t e
     return fast_clamp(h, v);
 }
 
-// T.87 A.12 / A.13 without the reference's sanity check (src/regular_mode_context.hpp:45-94); branch-light.
+// T.87 A.12 / A.13 (reference src/regular_mode_context.hpp:45-94); branch-light.  Returns non-zero where the reference's
+// sanity check (:52-54, a >= 2^24 or |b| >= 2^24 before the halving and clamping) fires; only the decoder looks at it.
+// With NEAR = 0, |b| stays below RESET + 65535 and is not tested.
 template<bool LOSSLESS>
-JLS_HD void fast_update_context(const HotParams& h, RegularContext& c, int32_t e)
+JLS_HD uint32_t fast_update_context(const HotParams& h, RegularContext& c, int32_t e)
 {
     c.a += iabs(e);
     c.b += LOSSLESS ? e : e * h.dq;
+    const uint32_t insane = static_cast<uint32_t>(LOSSLESS ? c.a : (c.a | iabs(c.b))) >> 24;
     if (JLS_UNLIKELY(c.n == h.reset))
     {
         c.a >>= 1;
@@ -133,6 +153,7 @@ JLS_HD void fast_update_context(const HotParams& h, RegularContext& c, int32_t e
     const int32_t c_high = imin(c.c + 1, 127);
     c.b = low ? b_low : (high ? b_high : c.b);
     c.c = low ? c_low : (high ? c_high : c.c);
+    return insane;
 }
 
 // Fills entry `index` of the context table (callers loop / stride over [0, last]).
@@ -471,12 +492,11 @@ struct FastReader
             refill();
         const uint32_t top = c3;
         const int32_t z = clz32(top);
-        const int32_t length = z + 1 + k;
-        if (JLS_LIKELY(z < escape && length <= 32))
+        if (JLS_LIKELY(z < imin(escape, 32 - k)))
         {
-            // the whole code word sits in the top 32 bits (valid > 32)
-            const uint32_t remainder = ((top << z) << 1) >> 1 >> (31 - k);
-            consume(length);
+            // not an escape and the whole code word (z + 1 + k bits) sits in the top 32 bits (valid > 32)
+            const uint32_t remainder = shr_sat(shl_sat(top, static_cast<uint32_t>(z + 1)), static_cast<uint32_t>(32 - k));
+            consume(z + 1 + k);
             return (z << k) + static_cast<int32_t>(remainder);
         }
         int32_t zeros = 0;
@@ -534,21 +554,59 @@ JLS_HD int32_t fast_decode_run_length(FastReader& br, int32_t& run_index, int32_
 template<int NC, bool USE_LUT>
 struct FastLineState
 {
-    RegularContext* contexts; // this thread's context q lives at contexts[q * context_stride]
+    RegularContext* contexts; // this thread's context q lives at contexts[q * context_stride] (device: shared memory)
     int32_t context_stride;
+#if defined(__CUDA_ARCH__)
+    uint32_t context_base; // shared-window address of contexts[0], see begin_interval
+#endif
     RegularContext cached;
     int32_t cached_index;
     RunContext run_context; // scalar lines only ever use RItype 1, multi-component pixels only RItype 0
     int32_t run_index;
     int32_t ra[NC];
 
+    JLS_HD void store_context(int32_t index, const RegularContext& c)
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};"
+                     :
+                     : "r"(context_base + static_cast<uint32_t>(index * context_stride) * 16U), "r"(c.a), "r"(c.b), "r"(c.c), "r"(c.n)
+                     : "memory");
+#else
+        contexts[index * context_stride] = c;
+#endif
+    }
+
+    JLS_HD RegularContext load_context(int32_t index) const
+    {
+#if defined(__CUDA_ARCH__)
+        RegularContext c;
+        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(c.a), "=r"(c.b), "=r"(c.c), "=r"(c.n)
+                     : "r"(context_base + static_cast<uint32_t>(index * context_stride) * 16U)
+                     : "memory");
+        return c;
+#else
+        return contexts[index * context_stride];
+#endif
+    }
+
     JLS_HD void begin_interval(const HotParams& h, RegularContext* ctx, int32_t stride)
     {
         contexts = ctx;
         context_stride = stride;
+#if defined(__CUDA_ARCH__)
+        // ptxas recomputes a shared address that derives from %tid at every use (S2R, S2UR, UMOV, ULEA, LEA: five issue
+        // slots per pixel) instead of holding it in a register.  A volatile round trip through the thread's own context
+        // slot makes the value opaque.
+        static_assert(sizeof(RegularContext) == 16, "one context is one 16-byte shared-memory access");
+        volatile uint32_t* own_slot = reinterpret_cast<volatile uint32_t*>(ctx);
+        *own_slot = static_cast<uint32_t>(__cvta_generic_to_shared(ctx));
+        context_base = *own_slot;
+#endif
         const RegularContext initial = {h.a_init, 0, 0, 1};
         for (int32_t q = 0; q < 5; ++q)
-            contexts[q * stride] = initial;
+            store_context(q, initial);
         cached = initial;
         cached_index = 4;
         run_context.a = h.a_init;
@@ -570,8 +628,8 @@ struct FastLineState
     {
         if (index != cached_index)
         {
-            contexts[cached_index * context_stride] = cached;
-            cached = contexts[index * context_stride];
+            store_context(cached_index, cached);
+            cached = load_context(index);
             cached_index = index;
         }
     }
@@ -749,19 +807,16 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
         RegularContext& c = this->cached;
         const bool negative = NC == 1 || q != 0;
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
-        int32_t k = golomb_parameter(c.a, c.n);
-        if (JLS_UNLIKELY(k >= 16)) // reference src/regular_mode_context.hpp:107-108
-        {
-            br.bad = 1;
-            k = 15;
-        }
+        const int32_t k = golomb_parameter(c.a, c.n);
+        // The reference rejects k >= 16 (src/regular_mode_context.hpp:107-108).  No branch and no clamp: the flag is
+        // sticky, a < 2^24 bounds k by 24 and the reader takes any k <= 31.
+        uint32_t insane = static_cast<uint32_t>(k) >> 4;
         const bool flip = k == 0 && (LOSSLESS || h.near == 0) && 2 * c.b + c.n < 1; // see the encoder
         const int32_t e = unmap_error_value(br.get_golomb(h, k, h.escape) ^ (flip ? 1 : 0));
-        fast_update_context<LOSSLESS>(h, c, e);
-        // the reference's sanity checks (src/scan_decoder_core.hpp:57-58, src/regular_mode_context.hpp:52-54)
-        // a >= 0; one test covers a >= 2^24, |b| >= 2^24 and |e| > 65535
-        if (JLS_UNLIKELY((((c.a | iabs(c.b)) >> 24) | (iabs(e) >> 16)) != 0))
-            br.bad = 1;
+        // the reference's sanity checks: |e| > 65535 (src/scan_decoder_core.hpp:57-58) and the context's (:52-54)
+        insane |= static_cast<uint32_t>(iabs(e)) >> 16;
+        insane |= fast_update_context<LOSSLESS>(h, c, e);
+        br.bad |= insane;
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }
 

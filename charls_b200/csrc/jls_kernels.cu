@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(fast_block_threads)
     const uint32_t interval = first_line + lane;
     const bool active = interval < p.interval_count;
 
+    __shared__ int32_t hot_scratch[warps][8];
     HotParams h = make_hot_params(p);
+    keep_hot_params_in_registers(h, hot_scratch[warp]);
     h.context_lut = context_lut;
     h.context_lut_last = lut_last;
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
@@ -203,7 +205,9 @@ __global__ void __launch_bounds__(fast_block_threads)
     }
     const uint32_t row_mask = __ballot_sync(0xFFFFFFFFU, coding);
 
-    const HotParams h = make_hot_params(p);
+    __shared__ int32_t hot_scratch[warps][8];
+    HotParams h = make_hot_params(p);
+    keep_hot_params_in_registers(h, hot_scratch[warp]);
     FastLineDecoder<NC, LOSSLESS, false> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
@@ -225,9 +229,14 @@ __global__ void __launch_bounds__(fast_block_threads)
             S* sample = reinterpret_cast<S*>(&tile[lane * SW]);
             const int32_t x0 = t * pixels_per_tile;
             S* const tile_end = sample + min(pixels_per_tile, width - x0) * NC;
-            for (int32_t left = width - x0; sample != tile_end; sample += NC, --left)
+            // pixels of the line that lie beyond this tile; the loop carries only the sample pointer: the refill
+            // cadence comes from its low bits and `left` is needed on the rare run-mode path only
+            const int32_t beyond = width - x0 - static_cast<int32_t>(tile_end - sample) / NC;
+            for (; sample != tile_end; sample += NC)
             {
-                if ((left & (refill_cadence - 1)) == 0)
+                const int32_t left = beyond + static_cast<int32_t>(tile_end - sample) / NC;
+                if (NC == 1 ? (reinterpret_cast<uintptr_t>(sample) & (refill_cadence * sizeof(S) - 1)) == 0
+                            : (left & (refill_cadence - 1)) == 0)
                     dec.top_up();
                 dec.pixel(h, left);
                 int32_t v[NC];
