@@ -36,6 +36,7 @@ struct HotParams
     // kernels keep it in shared memory: one LDS replaces three compares, a select and the adds on the busy ALU pipe.
     const uint8_t* context_lut;
     int32_t context_lut_last;
+    uint32_t context_lut_shared; // device: shared-window address of context_lut (see keep_hot_params_in_registers)
 };
 
 constexpr int32_t context_lut_capacity = 1024; // the table covers T3 <= 1023 (defaults: 21 / 85 / 276 for 8 / 12 / 16 bit)
@@ -60,6 +61,7 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.dq_magic = p.dq_magic;
     h.context_lut = nullptr;
     h.context_lut_last = 0;
+    h.context_lut_shared = 0;
     return h;
 }
 
@@ -67,7 +69,7 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
 // Moves the parameters the pixel loop reads into registers.  Kernel parameters live in the constant bank and ptxas
 // re-reads them (LDC / LDCU, one issue slot each) at every use instead of spending a register: 5 to 9 slots per pixel.
 // It also sees through shuffles and register moves of such warp-uniform values, so they take a round trip through
-// `scratch` (8 words of shared memory owned by the calling warp; all 32 lanes call this).
+// `scratch` (hot_scratch_words words of shared memory owned by the calling warp; all 32 lanes call this).
 __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volatile int32_t* scratch)
 {
     if ((threadIdx.x & 31U) == 0)
@@ -80,6 +82,7 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
         scratch[5] = h.escape;
         scratch[6] = h.maxval;
         scratch[7] = h.bits;
+        scratch[8] = static_cast<int32_t>(h.context_lut_shared);
     }
     __syncwarp();
     h.t1 = scratch[0];
@@ -90,7 +93,9 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
     h.escape = scratch[5];
     h.maxval = scratch[6];
     h.bits = scratch[7];
+    h.context_lut_shared = static_cast<uint32_t>(scratch[8]); // same story for an address that derives from the CTA id
 }
+constexpr int hot_scratch_words = 9;
 #endif
 
 template<bool LOSSLESS>
@@ -485,6 +490,33 @@ struct FastReader
         return (real_valid_bits > 0 ? real_valid_bits / 8 : 0) + (remaining > 0 ? remaining : 0);
     }
 
+    // The regular-mode symbols of a line are read under a contract that needs no refill test per symbol: the pixel loop
+    // tops the window up to > full_mark bits at least every `steady_symbols` symbols, the straight-line path below
+    // only takes code words of up to `steady_bits` bits (full_mark + 1 - 4 * 24 >= 24), and every other way of
+    // consuming bits (long code words, run mode) ends with a top_up() of its own.
+    static constexpr int32_t steady_bits = 24;
+    static constexpr int32_t steady_symbols = 4;
+
+    JLS_HD int32_t get_golomb_steady(const HotParams& h, int32_t k, int32_t escape)
+    {
+#if !defined(__CUDA_ARCH__)
+        if (valid < steady_bits)
+            bad = 0x80000000U; // contract broken: fails every host-emulation test
+#endif
+        const uint32_t top = c3;
+        const int32_t z = clz32(top);
+        if (JLS_LIKELY(z < imin(escape, steady_bits - k)))
+        {
+            // not an escape, and the code word (z + 1 + k <= steady_bits bits) is valid and sits in c3
+            const uint32_t remainder = shr_sat(shl_sat(top, static_cast<uint32_t>(z + 1)), static_cast<uint32_t>(32 - k));
+            consume(z + 1 + k);
+            return (z << k) + static_cast<int32_t>(remainder);
+        }
+        const int32_t value = get_golomb(h, k, escape);
+        top_up();
+        return value;
+    }
+
     // limited-length Golomb code (reference src/scan_decoder.hpp:113-125,203-217); `bad` on a malformed code
     JLS_HD int32_t get_golomb(const HotParams& h, int32_t k, int32_t escape)
     {
@@ -643,7 +675,15 @@ struct FastLineState
     static JLS_HD int32_t context_index(const HotParams& h, int32_t ra_value)
     {
         if (USE_LUT)
+        {
+#if defined(__CUDA_ARCH__)
+            uint32_t q;
+            asm("ld.shared.u8 %0, [%1];" : "=r"(q) : "r"(h.context_lut_shared + static_cast<uint32_t>(imin(ra_value, h.context_lut_last))));
+            return static_cast<int32_t>(q);
+#else
             return h.context_lut[imin(ra_value, h.context_lut_last)];
+#endif
+        }
         return context_index_compare(h, ra_value);
     }
 
@@ -812,7 +852,7 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
         // sticky, a < 2^24 bounds k by 24 and the reader takes any k <= 31.
         uint32_t insane = static_cast<uint32_t>(k) >> 4;
         const bool flip = k == 0 && (LOSSLESS || h.near == 0) && 2 * c.b + c.n < 1; // see the encoder
-        const int32_t e = unmap_error_value(br.get_golomb(h, k, h.escape) ^ (flip ? 1 : 0));
+        const int32_t e = unmap_error_value(br.get_golomb_steady(h, k, h.escape) ^ (flip ? 1 : 0));
         // the reference's sanity checks: |e| > 65535 (src/scan_decoder_core.hpp:57-58) and the context's (:52-54)
         insane |= static_cast<uint32_t>(iabs(e)) >> 16;
         insane |= fast_update_context<LOSSLESS>(h, c, e);
@@ -842,18 +882,18 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
         pending = 0;
     }
 
-    // Decodes one pixel into this->ra. `remaining` = pixels left in the line including this one.
-    JLS_HD void pixel(const HotParams& h, int32_t remaining)
+    // pixels between two top_up() calls of the pixel loop (FastReader::steady_symbols regular-mode symbols at most)
+    static constexpr int32_t pixels_per_top_up = NC == 1 ? 4 : NC == 2 ? 2 : 1;
+
+    // a pixel that belongs to a run, ends one or starts one
+    JLS_HD void run_mode_pixel(const HotParams& h, int32_t remaining)
     {
-        if (JLS_UNLIKELY(pending != 0))
+        if (pending > 1)
         {
-            if (pending > 1)
-                pending -= 2; // a pixel of the run: Ra stays
-            else
-                interruption(h);
+            pending -= 2; // a pixel of the run: Ra stays
             return;
         }
-        if (JLS_UNLIKELY(this->in_run_mode(h)))
+        if (pending == 0)
         {
             const int32_t length = fast_decode_run_length(br, this->run_index, remaining);
             if (length < 0)
@@ -865,10 +905,21 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
             if (length > 0)
             {
                 pending += 2 * (length - 1);
+                br.top_up();
                 return;
             }
-            if (pending != 0)
-                interruption(h);
+        }
+        if (pending != 0)
+            interruption(h);
+        br.top_up();
+    }
+
+    // Decodes one pixel into this->ra. `remaining` = pixels left in the line including this one.
+    JLS_HD void pixel(const HotParams& h, int32_t remaining)
+    {
+        if (JLS_UNLIKELY((pending != 0) | this->in_run_mode(h)))
+        {
+            run_mode_pixel(h, remaining);
             return;
         }
 #pragma unroll

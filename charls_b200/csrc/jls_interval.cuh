@@ -196,7 +196,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
                 dec.begin_line();
                 for (int32_t x = 0; x < width; ++x)
                 {
-                    if ((x & 3) == 0)
+                    if (x % dec.pixels_per_top_up == 0)
                         dec.top_up();
                     dec.pixel(h, width - x);
                     line[x * nc + c] = static_cast<S>(dec.ra[0]);
@@ -219,7 +219,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
     {
         for (int32_t x = 0; x < width; ++x)
         {
-            if ((x & 3) == 0)
+            if (x % dec.pixels_per_top_up == 0)
                 dec.top_up();
             dec.pixel(h, width - x);
             fast_store_pixel<NC, S>(p, line, x, dec.ra);

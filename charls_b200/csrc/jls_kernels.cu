@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(fast_block_threads)
     const uint32_t interval = first_line + lane;
     const bool active = interval < p.interval_count;
 
-    __shared__ int32_t hot_scratch[warps][8];
+    __shared__ int32_t hot_scratch[warps][hot_scratch_words];
     HotParams h = make_hot_params(p);
-    keep_hot_params_in_registers(h, hot_scratch[warp]);
     h.context_lut = context_lut;
     h.context_lut_last = lut_last;
+    h.context_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(context_lut));
+    keep_hot_params_in_registers(h, hot_scratch[warp]);
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
     FastLineEncoder<NC, LOSSLESS, true, !(LOSSLESS && sizeof(S) == 2)> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
@@ -143,8 +144,9 @@ __global__ void __launch_bounds__(fast_block_threads)
             uint32_t cadence = 0;
             for (; sample != tile_end; sample += NC)
             {
-                if ((++cadence & 3U) == 0)
-                    enc.drain(); // uniform across the warp
+                // every fourth pixel, for all lanes of the warp together; scalar lines take the count from the address
+                if (NC == 1 ? (reinterpret_cast<uintptr_t>(sample) & (4 * sizeof(S) - 1)) == 0 : (++cadence & 3U) == 0)
+                    enc.drain();
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
-    // pixels between two top-ups of the 128-bit read window (~4 bits per 8-bit sample on image data)
-    constexpr int refill_cadence = (NC == 1 && sizeof(S) == 1) ? 4 : 2;
+    // pixels between two top-ups of the 128-bit read window (see FastReader::get_golomb_steady)
+    constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, false>::pixels_per_top_up;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
 
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     }
     const uint32_t row_mask = __ballot_sync(0xFFFFFFFFU, coding);
 
-    __shared__ int32_t hot_scratch[warps][8];
+    __shared__ int32_t hot_scratch[warps][hot_scratch_words];
     HotParams h = make_hot_params(p);
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     FastLineDecoder<NC, LOSSLESS, false> dec;
