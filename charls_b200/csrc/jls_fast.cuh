@@ -669,7 +669,12 @@ struct FastLineState
     // |Q(-Ra)|: di = -Ra <= -T3 -> 4, <= -T2 -> 3, <= -T1 -> 2, < -NEAR -> 1, else 0 (jpegls_algorithm.hpp:173-194)
     static JLS_HD int32_t context_index_compare(const HotParams& h, int32_t ra_value)
     {
-        return (ra_value >= h.t3) + (ra_value >= h.t2) + (ra_value >= h.t1) + (ra_value > h.near);
+        // NEAR < T1 <= T2 <= T3 (checked with the preset parameters): a select chain, cheaper than adding four compares
+        int32_t q = ra_value > h.near ? 1 : 0;
+        q = ra_value >= h.t1 ? 2 : q;
+        q = ra_value >= h.t2 ? 3 : q;
+        q = ra_value >= h.t3 ? 4 : q;
+        return q;
     }
 
     static JLS_HD int32_t context_index(const HotParams& h, int32_t ra_value)
@@ -820,15 +825,17 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
     // register and one test on the regular-mode path
     int32_t pending;
+    uint32_t insane_seen; // sticky: one of the reference's sanity checks fired in regular mode
 
     JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, const uint8_t* begin_, const uint8_t* end_)
     {
         this->begin_interval(h, ctx, stride);
         br.init(begin_, end_);
         pending = 0;
+        insane_seen = 0;
     }
 
-    JLS_HD bool bad() const { return br.bad != 0; }
+    JLS_HD bool bad() const { return (br.bad | insane_seen) != 0; }
 
     // called by the pixel loop every few pixels, by all lanes at the same time (see FastReader)
     JLS_HD void top_up() { br.top_up(); }
@@ -856,7 +863,7 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
         // the reference's sanity checks: |e| > 65535 (src/scan_decoder_core.hpp:57-58) and the context's (:52-54)
         insane |= static_cast<uint32_t>(iabs(e)) >> 16;
         insane |= fast_update_context<LOSSLESS>(h, c, e);
-        br.bad |= insane;
+        insane_seen |= insane; // a flag of its own: br.bad is written on the rare paths and would be copied around them
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }
 

@@ -140,13 +140,12 @@ __global__ void __launch_bounds__(fast_block_threads)
         if (active)
         {
             const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
-            const S* const tile_end = sample + min(pixels_per_tile, width - t * pixels_per_tile) * NC;
-            uint32_t cadence = 0;
-            for (; sample != tile_end; sample += NC)
+            // two loop registers: the sample pointer and a count-down that is loop condition and drain cadence at once
+            int32_t n = min(pixels_per_tile, width - t * pixels_per_tile);
+            for (; n != 0; sample += NC, --n)
             {
-                // every fourth pixel, for all lanes of the warp together; scalar lines take the count from the address
-                if (NC == 1 ? (reinterpret_cast<uintptr_t>(sample) & (4 * sizeof(S) - 1)) == 0 : (++cadence & 3U) == 0)
-                    enc.drain();
+                if ((n & 3) == 0)
+                    enc.drain(); // every fourth pixel, for all lanes of the warp together
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -230,17 +229,15 @@ __global__ void __launch_bounds__(fast_block_threads)
         {
             S* sample = reinterpret_cast<S*>(&tile[lane * SW]);
             const int32_t x0 = t * pixels_per_tile;
-            S* const tile_end = sample + min(pixels_per_tile, width - x0) * NC;
-            // pixels of the line that lie beyond this tile; the loop carries only the sample pointer: the refill
-            // cadence comes from its low bits and `left` is needed on the rare run-mode path only
-            const int32_t beyond = width - x0 - static_cast<int32_t>(tile_end - sample) / NC;
-            for (; sample != tile_end; sample += NC)
+            // two loop registers: the sample pointer and a count-down that is loop condition and refill cadence at once;
+            // the pixels left in the line are needed on the rare run-mode path only
+            const int32_t beyond = max(width - x0 - pixels_per_tile, 0); // pixels of the line after this tile
+            int32_t n = width - x0 - beyond;
+            do
             {
-                const int32_t left = beyond + static_cast<int32_t>(tile_end - sample) / NC;
-                if (NC == 1 ? (reinterpret_cast<uintptr_t>(sample) & (refill_cadence * sizeof(S) - 1)) == 0
-                            : (left & (refill_cadence - 1)) == 0)
+                if ((n & (refill_cadence - 1)) == 0)
                     dec.top_up();
-                dec.pixel(h, left);
+                dec.pixel(h, beyond + n);
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -250,7 +247,8 @@ __global__ void __launch_bounds__(fast_block_threads)
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
                     sample[c] = static_cast<S>(v[c]);
-            }
+                sample += NC;
+            } while (--n != 0);
         }
         __syncwarp();
         tile_store<TW>(tile, pixels, stride, first_line, row_mask, row_bytes, t, lane);
