@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=32)
     ap.add_argument("--e2e-threads", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-phases", action="store_true", help="e2e: encode all frames, then decode all (default: per frame)")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -246,7 +247,7 @@ def workload_name(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
-def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads):
+def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads, pipelined=True):
     """Through the C ABI with pinned host buffers: every frame encoded, then every stream decoded. Returns (s, sizes)."""
     from charls_b200.capi import FrameInfo
 
@@ -277,10 +278,19 @@ def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads):
         lib.check(lib.charls_jpegls_decoder_decode_to_buffer(d, out_host[i].data_ptr(), frame_bytes, 0))
         lib.charls_jpegls_decoder_destroy(d)
 
+    def both(i):
+        enc(i)
+        dec(i)
+
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as pool:
-        list(pool.map(enc, range(n)))
-        list(pool.map(dec, range(n)))
+        if pipelined:
+            # every worker encodes a frame and decodes it right away: both PCIe directions carry raw and compressed
+            # bytes all the time instead of raw going up in one phase and coming down in the next
+            list(pool.map(both, range(n)))
+        else:
+            list(pool.map(enc, range(n)))
+            list(pool.map(dec, range(n)))
     return time.perf_counter() - t0, sizes
 
 
@@ -382,13 +392,13 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         threads = max(1, min(args.e2e_threads, effective_cpus()))
         for _ in range(3):
-            e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads)
+            e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads, not args.e2e_phases)
         if world > 1:
             dist.barrier()
         t_e2e, e2e_sizes = 0.0, None
         reps = max(3, args.steps)
         for _ in range(reps):
-            dt, e2e_sizes = e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads)
+            dt, e2e_sizes = e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads, not args.e2e_phases)
             t_e2e += dt
         if near == 0:
             assert torch.equal(out_host, frames_host), "e2e round trip mismatch"
@@ -400,6 +410,7 @@ def run_gpu_arm(args):
             "value": world * n * w * h / float(t.item()) / 1e6, "unit": "MPixels/s",
             "h2d_bytes_per_step": world * (n * raw_bytes + comp), "d2h_bytes_per_step": world * (comp + n * raw_bytes),
             "frames_per_step": world * n, "host_threads": threads,
+            "order": "all frames encoded, then all decoded" if args.e2e_phases else "each frame encoded and decoded by one worker",
             "api": "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
         }
 

@@ -13,7 +13,8 @@ import os
 from ctypes import POINTER, byref, c_char_p, c_int32, c_size_t, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.path.join(_HERE, "lib", "libcharls.so.3")
+# CHARLS_B200_LIBRARY points the package at another build of the same library (tools/ab_build.py: kernel experiments)
+DEFAULT_LIBRARY = os.environ.get("CHARLS_B200_LIBRARY") or os.path.join(_HERE, "lib", "libcharls.so.3")
 
 
 class FrameInfo(C.Structure):

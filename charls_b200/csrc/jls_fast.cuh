@@ -669,12 +669,8 @@ struct FastLineState
     // |Q(-Ra)|: di = -Ra <= -T3 -> 4, <= -T2 -> 3, <= -T1 -> 2, < -NEAR -> 1, else 0 (jpegls_algorithm.hpp:173-194)
     static JLS_HD int32_t context_index_compare(const HotParams& h, int32_t ra_value)
     {
-        // NEAR < T1 <= T2 <= T3 (checked with the preset parameters): a select chain, cheaper than adding four compares
-        int32_t q = ra_value > h.near ? 1 : 0;
-        q = ra_value >= h.t1 ? 2 : q;
-        q = ra_value >= h.t2 ? 3 : q;
-        q = ra_value >= h.t3 ? 4 : q;
-        return q;
+        // four independent compares: a select chain has fewer instructions but its latency sits on the critical path
+        return (ra_value >= h.t3) + (ra_value >= h.t2) + (ra_value >= h.t1) + (ra_value > h.near);
     }
 
     static JLS_HD int32_t context_index(const HotParams& h, int32_t ra_value)

@@ -183,6 +183,12 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, false>::pixels_per_top_up;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
+    __shared__ uint8_t context_lut[context_lut_capacity];
+
+    const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
+    for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
+        context_lut[i] = context_lut_entry(p, i);
+    __syncthreads();
 
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,8 +214,11 @@ __global__ void __launch_bounds__(fast_block_threads)
 
     __shared__ int32_t hot_scratch[warps][hot_scratch_words];
     HotParams h = make_hot_params(p);
+    h.context_lut = context_lut;
+    h.context_lut_last = lut_last;
+    h.context_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(context_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
-    FastLineDecoder<NC, LOSSLESS, false> dec;
+    FastLineDecoder<NC, LOSSLESS, true> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
     dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
@@ -233,11 +242,22 @@ __global__ void __launch_bounds__(fast_block_threads)
             // the pixels left in the line are needed on the rare run-mode path only
             const int32_t beyond = max(width - x0 - pixels_per_tile, 0); // pixels of the line after this tile
             int32_t n = width - x0 - beyond;
+#if defined(JLS_AB_DEC_PTR_LOOP)
+            S* const tile_end = sample + n * NC;
+            for (; sample != tile_end;)
+            {
+                const int32_t left = beyond + static_cast<int32_t>(tile_end - sample) / NC;
+                if (NC == 1 ? (reinterpret_cast<uintptr_t>(sample) & (refill_cadence * sizeof(S) - 1)) == 0
+                            : (left & (refill_cadence - 1)) == 0)
+                    dec.top_up();
+                dec.pixel(h, left);
+#else
             do
             {
                 if ((n & (refill_cadence - 1)) == 0)
                     dec.top_up();
                 dec.pixel(h, beyond + n);
+#endif
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -248,7 +268,11 @@ __global__ void __launch_bounds__(fast_block_threads)
                 for (int32_t c = 0; c < NC; ++c)
                     sample[c] = static_cast<S>(v[c]);
                 sample += NC;
+#if defined(JLS_AB_DEC_PTR_LOOP)
+            }
+#else
             } while (--n != 0);
+#endif
         }
         __syncwarp();
         tile_store<TW>(tile, pixels, stride, first_line, row_mask, row_bytes, t, lane);

@@ -1,0 +1,67 @@
+"""Where does the end-to-end time go?  Per-call latency of the C-ABI encode / decode calls with pinned host buffers at
+several thread counts (cfg2 frames).  Prints one line per thread count."""
+import ctypes as C
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from charls_b200 import capi  # noqa: E402
+from charls_b200.capi import FrameInfo  # noqa: E402
+
+lib = capi.default_library()
+w = h = 4096
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+frames = bench.make_frames(torch, torch.device("cuda"), n, "cfg2", 1234)
+frames_host = frames.cpu().pin_memory()
+cap = w * h * 2 + 65536
+streams_host = torch.empty((n, cap), dtype=torch.uint8).pin_memory()
+out_host = torch.empty_like(frames_host).pin_memory()
+sizes = [0] * n
+t_enc = [0.0] * n
+t_dec = [0.0] * n
+frame_bytes = w * h
+
+
+def enc(i):
+    t0 = time.perf_counter()
+    e = lib.charls_jpegls_encoder_create()
+    fi = FrameInfo(w, h, 8, 1)
+    lib.check(lib.charls_jpegls_encoder_set_frame_info(e, C.byref(fi)))
+    lib.check(lib.charls_jpegls_encoder_set_destination_buffer(e, streams_host[i].data_ptr(), cap))
+    lib.check(lib.charls_jpegls_encoder_encode_from_buffer(e, frames_host[i].data_ptr(), frame_bytes, 0))
+    written = C.c_size_t()
+    lib.check(lib.charls_jpegls_encoder_get_bytes_written(e, C.byref(written)))
+    lib.charls_jpegls_encoder_destroy(e)
+    sizes[i] = written.value
+    t_enc[i] = time.perf_counter() - t0
+
+
+def dec(i):
+    t0 = time.perf_counter()
+    d = lib.charls_jpegls_decoder_create()
+    lib.check(lib.charls_jpegls_decoder_set_source_buffer(d, streams_host[i].data_ptr(), sizes[i]))
+    lib.check(lib.charls_jpegls_decoder_read_header(d))
+    lib.check(lib.charls_jpegls_decoder_decode_to_buffer(d, out_host[i].data_ptr(), frame_bytes, 0))
+    lib.charls_jpegls_decoder_destroy(d)
+    t_dec[i] = time.perf_counter() - t0
+
+
+def both(i):
+    enc(i)
+    dec(i)
+
+
+for threads in (1, 4, 8, 16, 32):
+    for rep in range(3):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(both, range(n)))
+        dt = time.perf_counter() - t0
+    print(f"threads {threads:2d}: {n * w * h / dt / 1e9:6.2f} GPix/s  step {dt * 1e3:7.2f} ms  "
+          f"enc call {sum(t_enc) / n * 1e3:6.2f} ms  dec call {sum(t_dec) / n * 1e3:6.2f} ms  ratio {w * h / (sum(sizes) / n):.2f}")
+assert torch.equal(out_host, frames_host)
