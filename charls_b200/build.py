@@ -77,7 +77,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    build_driver(force, verbose)
     return LIB
+
+
+DRIVER = os.path.join(LIB_DIR, "libabi_driver.so")
+
+
+def build_driver(force: bool = False, verbose: bool = False) -> str:
+    """charls_b200/lib/libabi_driver.so: plain C++ threads that call a CharLS-compatible C ABI (csrc/driver)."""
+    src = os.path.join(CSRC, "driver", "abi_driver.cpp")
+    if force or _stale(DRIVER, [src]):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-Wextra", "-o", DRIVER, src, "-ldl",
+               "-lpthread", "-static-libstdc++", "-static-libgcc"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return DRIVER
 
 
 if __name__ == "__main__":

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 #include <mutex>
@@ -86,6 +87,9 @@ Engine::~Engine()
     for (auto& event : events_)
         if (event)
             cudaEventDestroy(event);
+    drop_graphs();
+    if (sleep_event_)
+        cudaEventDestroy(sleep_event_);
     if (stream_)
         cudaStreamDestroy(stream_);
 }
@@ -94,10 +98,13 @@ namespace {
 std::mutex g_pool_mutex;
 std::vector<Engine*> g_pool;
 constexpr size_t pool_limit = 64;
+std::atomic<int> g_borrowed{0};           // engines that codec objects hold right now
+constexpr int blocking_sync_threshold = 6; // see Engine::wait_for
 } // namespace
 
 Engine* Engine::acquire()
 {
+    g_borrowed.fetch_add(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lock(g_pool_mutex);
         if (!g_pool.empty())
@@ -114,6 +121,7 @@ void Engine::release(Engine* engine) noexcept
 {
     if (!engine)
         return;
+    g_borrowed.fetch_sub(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lock(g_pool_mutex);
         if (g_pool.size() < pool_limit && (g_device.load() < 0 || engine->device_ < 0 || engine->device_ == g_device.load()))
@@ -123,6 +131,29 @@ void Engine::release(Engine* engine) noexcept
         }
     }
     delete engine;
+}
+
+// Waits until `stream` has drained.  A lone caller spins (lowest latency).  When many codec objects are in flight -- one
+// host thread per image is how the reference API gets used in parallel -- spinning threads eat the cores (and any CPU
+// quota of the container) the other callers need to feed the GPU, so from `blocking_sync_threshold` borrowed engines on
+// the thread sleeps on an event instead.  CHARLS_B200_BLOCKING_SYNC=0 / 1 forces one behaviour.
+int32_t Engine::wait_for(CUstream_st* stream)
+{
+    static const int forced = [] {
+        const char* value = std::getenv("CHARLS_B200_BLOCKING_SYNC");
+        return value && (value[0] == '0' || value[0] == '1') ? value[0] - '0' : -1;
+    }();
+    const bool blocking = forced >= 0 ? forced == 1 : g_borrowed.load(std::memory_order_relaxed) >= blocking_sync_threshold;
+    if (!blocking)
+    {
+        JLS_CUDA(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    if (!sleep_event_)
+        JLS_CUDA(cudaEventCreateWithFlags(&sleep_event_, cudaEventBlockingSync | cudaEventDisableTiming));
+    JLS_CUDA(cudaEventRecord(sleep_event_, stream));
+    JLS_CUDA(cudaEventSynchronize(sleep_event_));
+    return 0;
 }
 
 void Engine::read_coder_time() noexcept
@@ -170,6 +201,7 @@ int32_t Engine::ensure(Buffer& buffer, size_t bytes, bool pinned)
     if (buffer.capacity >= bytes && buffer.data)
         return 0;
     release(buffer);
+    ++buffer_generation_; // captured graphs hold the old address
     const size_t capacity = align_up(bytes + bytes / 8 + 256, 256);
     void* data = nullptr;
     if (pinned)
@@ -182,7 +214,8 @@ int32_t Engine::ensure(Buffer& buffer, size_t bytes, bool pinned)
     return 0;
 }
 
-int32_t Engine::stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream)
+int32_t Engine::stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream,
+                           bool upload)
 {
     const size_t n = jobs.size();
     const size_t intervals = p.interval_count;
@@ -214,7 +247,75 @@ int32_t Engine::stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, boo
         job.result = job.status + 1;
     }
     std::memcpy(host_jobs_.data, jobs.data(), n * sizeof(ScanJob));
-    JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, n * sizeof(ScanJob), cudaMemcpyHostToDevice, stream));
+    if (upload)
+        JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, n * sizeof(ScanJob), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Graph replay for the single-image calls
+// ---------------------------------------------------------------------------------------------------------------------
+void Engine::drop_graphs() noexcept
+{
+    for (CachedGraph& g : graphs_)
+        cudaGraphExecDestroy(g.exec);
+    graphs_.clear();
+}
+
+// `enqueue` issues work on stream_ only, reads and writes engine buffers only (their addresses are part of the captured
+// graph; `key` must cover every by-value kernel argument) and makes no synchronising call.  CHARLS_B200_GRAPHS=0 turns
+// the replay off (every call enqueues directly).
+template<typename Enqueue>
+int32_t Engine::replay(const GraphKey& key, Enqueue&& enqueue)
+{
+    static const bool enabled = [] {
+        const char* value = std::getenv("CHARLS_B200_GRAPHS");
+        return !(value && value[0] == '0');
+    }();
+    if (!enabled)
+        return enqueue();
+
+    if (!graphs_.empty() && graphs_.front().generation != buffer_generation_)
+        drop_graphs(); // a buffer moved
+    for (const CachedGraph& g : graphs_)
+    {
+        if (std::memcmp(&g.key, &key, sizeof(GraphKey)) == 0)
+        {
+            JLS_CUDA(cudaGraphLaunch(g.exec, stream_));
+            count_kernel_launches(g.launches);
+            return 0;
+        }
+    }
+
+    const uint64_t launches_before = thread_kernel_launch_count();
+    JLS_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    const int32_t status = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t end = cudaStreamEndCapture(stream_, &graph);
+    const uint32_t launches = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
+    if (status != 0 || end != cudaSuccess || !graph)
+    {
+        if (graph)
+            cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return status != 0 ? status : 200;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t made = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (made != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 200;
+    }
+    constexpr size_t graph_cache_limit = 8;
+    if (graphs_.size() >= graph_cache_limit)
+    {
+        cudaGraphExecDestroy(graphs_.front().exec);
+        graphs_.erase(graphs_.begin());
+    }
+    graphs_.push_back(CachedGraph{key, buffer_generation_, exec, launches});
+    JLS_CUDA(cudaGraphLaunch(exec, stream_));
     return 0;
 }
 
@@ -223,7 +324,7 @@ int32_t Engine::fetch_outcomes(size_t job_count, CUstream_st* stream)
     JLS_CHECK(ensure(host_outcomes_, job_count * outcome_words * sizeof(uint64_t), true));
     JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, job_count * outcome_words * sizeof(uint64_t),
                              cudaMemcpyDeviceToHost, stream));
-    JLS_CUDA(cudaStreamSynchronize(stream));
+    JLS_CHECK(wait_for(stream));
     return 0;
 }
 
@@ -235,7 +336,7 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
 {
     written = 0;
     JLS_CHECK(prepare());
-    const uint64_t launches_before = kernel_launch_count();
+    const uint64_t launches_before = thread_kernel_launch_count();
     const size_t row_bytes = row_bytes_of(p);
     const size_t pitch = align_up(row_bytes, 16);
     JLS_CHECK(ensure(pixels_, pitch * static_cast<size_t>(p.height) + 64));
@@ -259,11 +360,22 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     jobs[0].stride = pitch;
     jobs[0].stream_out = static_cast<uint8_t*>(stream_buffer_.data);
     jobs[0].stream_out_capacity = device_capacity;
-    JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_));
-    JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, events_, true));
-    JLS_CHECK(fetch_outcomes(1, stream_));
-    read_coder_time();
-    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+    JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_, false));
+    JLS_CHECK(ensure(host_outcomes_, outcome_words * sizeof(uint64_t), true));
+    GraphKey key{};
+    key.p = p;
+    key.slot_bytes = slot_bytes;
+    key.encode = 1;
+    JLS_CHECK(replay(key, [&]() -> int32_t {
+        JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, sizeof(ScanJob), cudaMemcpyHostToDevice, stream_));
+        JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, nullptr, true));
+        JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                 stream_));
+        return 0;
+    }));
+    JLS_CHECK(wait_for(stream_));
+    last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
     const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
     if (outcome[0] != ~0ULL)
@@ -274,7 +386,7 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     if (total != 0)
     {
         JLS_CUDA(cudaMemcpyAsync(destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
-        JLS_CUDA(cudaStreamSynchronize(stream_));
+        JLS_CHECK(wait_for(stream_));
     }
     written = static_cast<size_t>(total);
     return 0;
@@ -295,13 +407,16 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     JLS_CHECK(prepare());
     if (offset > uploaded_stream_size_)
         return err_need_more_data;
-    const uint64_t launches_before = kernel_launch_count();
+    const uint64_t launches_before = thread_kernel_launch_count();
     const size_t remaining = uploaded_stream_size_ - offset;
     const size_t row_bytes = row_bytes_of(p);
     const size_t pitch = align_up(row_bytes, 16);
     JLS_CHECK(ensure(pixels_, pitch * static_cast<size_t>(p.height) + 64));
 
-    const size_t blocks = marker_blocks_for(remaining);
+    // the marker kernels take their bounds from the job; sizing their grid for the next MiB lets streams of similar
+    // size share one captured graph
+    const size_t grid_bytes = align_up(remaining + 1, size_t{1} << 20);
+    const size_t blocks = marker_blocks_for(grid_bytes);
     JLS_CHECK(ensure(marker_counts_, (blocks + 1) * sizeof(uint32_t)));
     JLS_CHECK(ensure(marker_totals_, sizeof(uint32_t)));
     JLS_CHECK(ensure(marker_codes_, p.interval_count));
@@ -312,13 +427,23 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     jobs[0].stride = pitch;
     jobs[0].stream_in = static_cast<const uint8_t*>(stream_buffer_.data) + offset;
     jobs[0].stream_in_size = remaining;
-    JLS_CHECK(stage_jobs(p, jobs, false, 0, stream_));
-    JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), 1, remaining,
-                           static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                           static_cast<uint8_t*>(marker_codes_.data), stream_, events_, true));
-    JLS_CHECK(fetch_outcomes(1, stream_));
-    read_coder_time();
-    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+    JLS_CHECK(stage_jobs(p, jobs, false, 0, stream_, false));
+    JLS_CHECK(ensure(host_outcomes_, outcome_words * sizeof(uint64_t), true));
+    GraphKey key{};
+    key.p = p;
+    key.marker_blocks = blocks;
+    JLS_CHECK(replay(key, [&]() -> int32_t {
+        JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, sizeof(ScanJob), cudaMemcpyHostToDevice, stream_));
+        JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), 1, grid_bytes,
+                               static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
+                               static_cast<uint8_t*>(marker_codes_.data), stream_, nullptr, true));
+        JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                 stream_));
+        return 0;
+    }));
+    JLS_CHECK(wait_for(stream_));
+    last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
     const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
     if (outcome[0] != ~0ULL)
@@ -326,7 +451,7 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     consumed = static_cast<size_t>(outcome[1]);
     JLS_CUDA(cudaMemcpy2DAsync(destination, stride, pixels_.data, pitch, row_bytes, static_cast<size_t>(p.height),
                                cudaMemcpyDeviceToHost, stream_));
-    JLS_CUDA(cudaStreamSynchronize(stream_));
+    JLS_CHECK(wait_for(stream_));
     return 0;
 }
 
@@ -340,7 +465,7 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     if (count == 0)
         return 0;
     cudaStream_t stream = user_stream ? user_stream : stream_;
-    const uint64_t launches_before = kernel_launch_count();
+    const uint64_t launches_before = thread_kernel_launch_count();
     const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
     if (slot_bytes >= (size_t{1} << 32))
         return 7; // parameter_value_not_supported, see encode_scan_from_host
@@ -370,7 +495,7 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
                                 static_cast<uint32_t>(count), stream));
     JLS_CHECK(fetch_outcomes(count, stream));
     read_coder_time();
-    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
     int32_t first_error = 0;
     const uint64_t* outcomes = static_cast<const uint64_t*>(host_outcomes_.data);
@@ -410,7 +535,7 @@ int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32
     JLS_CUDA(launch_copy_prefixes(device_pointers, reinterpret_cast<const size_t*>(device_pointers + count),
                                   static_cast<uint8_t*>(prefixes_.data), prefix_bytes, static_cast<uint32_t>(count), stream));
     JLS_CUDA(cudaMemcpyAsync(host_prefixes_.data, prefixes_.data, count * prefix_bytes, cudaMemcpyDeviceToHost, stream));
-    JLS_CUDA(cudaStreamSynchronize(stream));
+    JLS_CHECK(wait_for(stream));
     prefixes.assign(static_cast<const uint8_t*>(host_prefixes_.data),
                     static_cast<const uint8_t*>(host_prefixes_.data) + count * prefix_bytes);
     return 0;
@@ -422,7 +547,7 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     if (count == 0)
         return 0;
     cudaStream_t stream = user_stream ? user_stream : stream_;
-    const uint64_t launches_before = kernel_launch_count();
+    const uint64_t launches_before = thread_kernel_launch_count();
 
     size_t max_remaining = 0;
     bool word_aligned = stride % 4 == 0;
@@ -448,7 +573,7 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
                            static_cast<uint8_t*>(marker_codes_.data), stream, events_, word_aligned));
     JLS_CHECK(fetch_outcomes(count, stream));
     read_coder_time();
-    last_launches_ = static_cast<uint32_t>(kernel_launch_count() - launches_before);
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
     int32_t first_error = 0;
     const uint64_t* outcomes = static_cast<const uint64_t*>(host_outcomes_.data);

@@ -16,6 +16,7 @@
 
 struct CUstream_st;
 struct CUevent_st;
+struct CUgraphExec_st;
 
 namespace jls {
 
@@ -85,9 +86,34 @@ private:
     int32_t ensure(Buffer& buffer, size_t bytes, bool pinned = false);
     void release(Buffer& buffer) noexcept;
     // Lays out the per-job scratch for `job_count` jobs and uploads the job table. Scratch pointers are filled in here.
-    int32_t stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream);
+    // `upload` false: the caller copies host_jobs_ to job_table_ itself (inside a replayed graph).
+    int32_t stage_jobs(const CodecParams& p, std::vector<ScanJob>& jobs, bool encode, size_t slot_bytes, CUstream_st* stream,
+                       bool upload = true);
     int32_t fetch_outcomes(size_t job_count, CUstream_st* stream);
+
+    // The single-image calls issue the same dozen launches and copies between engine buffers for every image of a
+    // series.  They are captured into a CUDA graph once and replayed: one driver call instead of twelve, which matters
+    // when many host threads code images at the same time (the driver serialises their calls).
+    struct GraphKey
+    {
+        CodecParams p;
+        uint64_t slot_bytes;
+        uint64_t marker_blocks;
+        uint32_t encode;
+        uint32_t reserved;
+    };
+    struct CachedGraph
+    {
+        GraphKey key;
+        uint64_t generation; // of the engine's buffers, see ensure()
+        CUgraphExec_st* exec;
+        uint32_t launches; // kernels inside
+    };
+    template<typename Enqueue>
+    int32_t replay(const GraphKey& key, Enqueue&& enqueue);
+    void drop_graphs() noexcept;
     void read_coder_time() noexcept;
+    int32_t wait_for(CUstream_st* stream);
 
     CUstream_st* stream_{};
     int device_{-1};
@@ -98,6 +124,9 @@ private:
     uint32_t last_launches_{};
     float last_coder_ms_{};
     CUevent_st* events_[2]{};
+    CUevent_st* sleep_event_{};
+    std::vector<CachedGraph> graphs_;
+    uint64_t buffer_generation_{};
 };
 
 } // namespace jls

@@ -21,10 +21,14 @@ namespace jls {
 
 namespace {
 
-constexpr int fast_block_threads = 128;
+#if !defined(JLS_FAST_BLOCK_THREADS)
+#define JLS_FAST_BLOCK_THREADS 32
+#endif
+constexpr int fast_block_threads = JLS_FAST_BLOCK_THREADS;
 constexpr int general_block_threads = 32;
 
 std::atomic<uint64_t> g_kernel_launches{0};
+thread_local uint64_t t_kernel_launches = 0; // launches issued by this host thread
 
 // first error in stream order wins: key = (interval << 8) | errc, smaller interval first
 __device__ __forceinline__ void report_error(const ScanJob& job, uint32_t interval, int32_t errc)
@@ -669,6 +673,7 @@ cudaError_t launch(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, Ar
 {
     kernel<<<grid, block, 0, stream>>>(args...);
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    ++t_kernel_launches;
     return cudaGetLastError();
 }
 
@@ -773,6 +778,17 @@ cudaError_t dispatch_decode_fast(const CodecParams& p, bool rows_word_aligned, d
 uint64_t kernel_launch_count() noexcept
 {
     return g_kernel_launches.load(std::memory_order_relaxed);
+}
+
+uint64_t thread_kernel_launch_count() noexcept
+{
+    return t_kernel_launches;
+}
+
+void count_kernel_launches(uint32_t launches) noexcept
+{
+    g_kernel_launches.fetch_add(launches, std::memory_order_relaxed);
+    t_kernel_launches += launches;
 }
 
 size_t marker_blocks_for(size_t stream_bytes) noexcept

@@ -9,7 +9,10 @@
 namespace jls {
 
 // Number of kernels this library has launched in this process (evidence for bench.py's "gpu_launches").
-uint64_t kernel_launch_count() noexcept;
+uint64_t kernel_launch_count() noexcept;        // process-wide
+uint64_t thread_kernel_launch_count() noexcept; // issued by the calling host thread
+// kernels that ran without going through launch(): the replay of a captured graph
+void count_kernel_launches(uint32_t launches) noexcept;
 
 // Blocks (of 4096 stream bytes) the marker kernels use for a stream of `stream_bytes`.
 size_t marker_blocks_for(size_t stream_bytes) noexcept;

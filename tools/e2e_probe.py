@@ -56,7 +56,7 @@ def both(i):
     dec(i)
 
 
-for threads in (1, 4, 8, 16, 32):
+for threads in ([int(t) for t in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1, 4, 8, 16, 32)):
     for rep in range(3):
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=threads) as pool:
@@ -65,3 +65,38 @@ for threads in (1, 4, 8, 16, 32):
     print(f"threads {threads:2d}: {n * w * h / dt / 1e9:6.2f} GPix/s  step {dt * 1e3:7.2f} ms  "
           f"enc call {sum(t_enc) / n * 1e3:6.2f} ms  dec call {sum(t_dec) / n * 1e3:6.2f} ms  ratio {w * h / (sum(sizes) / n):.2f}")
 assert torch.equal(out_host, frames_host)
+
+# ---- the same round trips from C++ threads (charls_b200/csrc/driver): no interpreter lock between the ABI calls
+from charls_b200 import driver  # noqa: E402
+
+for threads in (1, 4, 8, 16, 32):
+    for rep in range(3):
+        out_host.zero_()
+        dt, sizes_c = driver.run_round_trips(capi.DEFAULT_LIBRARY, frames_host.data_ptr(), frame_bytes, streams_host.data_ptr(), cap,
+                                            out_host.data_ptr(), n, threads, width=w, height=h, bits_per_sample=8)
+    assert torch.equal(out_host, frames_host)
+    print(f"C++ driver, threads {threads:2d}: {n * w * h / dt / 1e9:6.2f} GPix/s  step {dt * 1e3:7.2f} ms")
+
+# ---- the same round trips with frames and streams resident in HBM (no PCIe): one BatchCodec and CUDA stream per thread
+from charls_b200.batch import BatchCodec  # noqa: E402
+
+frames_dev = frames
+for threads in (1, 4, 8, 16):
+    codecs = [BatchCodec(w, h, 8) for _ in range(threads)]
+    cuda_streams = [torch.cuda.Stream() for _ in range(threads)]
+    bufs = [torch.empty((1, codecs[0].stream_capacity), dtype=torch.uint8, device="cuda") for _ in range(threads)]
+    outs = [torch.empty((1, h, w), dtype=torch.uint8, device="cuda") for _ in range(threads)]
+
+    def device_round_trip(k):
+        for i in range(k, n, threads):
+            sz = codecs[k].encode(frames_dev[i : i + 1], bufs[k], stream=cuda_streams[k])
+            codecs[k].decode(bufs[k], sz, outs[k], stream=cuda_streams[k])
+        cuda_streams[k].synchronize()
+
+    for rep in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(device_round_trip, range(threads)))
+        dt = time.perf_counter() - t0
+    print(f"device-resident, threads {threads:2d}: {n * w * h / dt / 1e9:6.2f} GPix/s  {n / dt:7.0f} frames/s")
