@@ -300,3 +300,33 @@ def test_batch_interface(product, oracle):
     with pytest.raises(CharlsError) as info:
         bc.encode(t, streams)
     assert info.value.errc == 3
+
+
+def test_series_of_images_replays_captured_graphs(product, oracle):
+    """The single-image calls replay a captured CUDA graph for every image after the first of a kind
+    (charls_b200/csrc/engine.cu, Engine::replay): same bytes as the oracle whatever the order of sizes and contents."""
+    makers = (s_noise, s_smooth, s_mixed, s_smooth, s_noise, s_mixed)
+    for (h, w, bits) in ((1000, 1200, 8), (61, 333, 12)):
+        for round_ in range(2):
+            for k, make in enumerate(makers):
+                image = make(h, w, bits, seed=100 * round_ + k)
+                stream = encode(product, image, bits)
+                assert payloads(stream) == payloads(oracle.encode_image(image, bits, ri=1)), (h, w, bits, round_, k)
+                pixels, _, _ = codec.decode(stream, lib=product)
+                assert np.array_equal(pixels, image), (h, w, bits, round_, k)
+
+
+def test_cpp_driver_round_trips(product):
+    """charls_b200/lib/libabi_driver.so: C++ threads on the C ABI, the way bench.py's probes drive it."""
+    from charls_b200 import driver
+
+    n, h, w = 12, 96, 160
+    frames = np.stack([s_mixed(h, w, 8, seed=i) for i in range(n)])
+    streams = np.zeros((n, 2 * h * w + 4096), np.uint8)
+    for per_frame in (True, False):
+        out = np.zeros_like(frames)
+        seconds, sizes = driver.run_round_trips(product.path, frames.ctypes.data, h * w, streams.ctypes.data, streams.shape[1],
+                                                out.ctypes.data, n, 4, width=w, height=h, bits_per_sample=8, per_frame=per_frame)
+        assert seconds > 0 and np.array_equal(out, frames)
+        for i in range(n):
+            assert streams[i, : sizes[i]].tobytes() == encode(product, frames[i], 8)
