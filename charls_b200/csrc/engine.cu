@@ -5,6 +5,10 @@
 #include "jls_kernels.hpp"
 
 #include <atomic>
+#include <chrono>
+#include <functional>
+#include <string>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -88,6 +92,9 @@ Engine::~Engine()
         if (event)
             cudaEventDestroy(event);
     drop_graphs();
+    for (auto& event : trace_events_)
+        if (event)
+            cudaEventDestroy(event);
     if (sleep_event_)
         cudaEventDestroy(sleep_event_);
     if (stream_)
@@ -98,6 +105,58 @@ namespace {
 std::mutex g_pool_mutex;
 std::vector<Engine*> g_pool;
 constexpr size_t pool_limit = 64;
+// CHARLS_B200_TRACE=<file>: a timeline of the single-image calls (host clock and CUDA events against one base event),
+// written when the library is unloaded.  tools/e2e_timeline.py reads it.  Costs nothing when the variable is not set.
+struct TraceRecord
+{
+    uint64_t thread;
+    int32_t kind; // 0 encode, 1 decode
+    double host_ms[4]; // call entered, work enqueued, outcome known, call done
+    float gpu_ms[4];   // stream reached the call, input copy done, kernels done, output copy done
+};
+
+struct Trace
+{
+    bool enabled = false;
+    std::string path;
+    std::mutex mutex;
+    std::vector<TraceRecord> records;
+    cudaEvent_t base = nullptr;
+    std::chrono::steady_clock::time_point start;
+
+    Trace()
+    {
+        const char* value = std::getenv("CHARLS_B200_TRACE");
+        if (value && value[0])
+        {
+            enabled = true;
+            path = value;
+            start = std::chrono::steady_clock::now();
+        }
+    }
+    ~Trace()
+    {
+        if (!enabled)
+            return;
+        if (FILE* f = std::fopen(path.c_str(), "w"))
+        {
+            for (const TraceRecord& r : records)
+                std::fprintf(f, "%llu %d %.4f %.4f %.4f %.4f %.4f %.4f %.4f %.4f\n", static_cast<unsigned long long>(r.thread),
+                             r.kind, r.host_ms[0], r.host_ms[1], r.host_ms[2], r.host_ms[3], r.gpu_ms[0], r.gpu_ms[1], r.gpu_ms[2],
+                             r.gpu_ms[3]);
+            std::fclose(f);
+        }
+    }
+    double now() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start).count(); }
+};
+Trace g_trace;
+
+// Streams are multiplexed onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue wait
+// for each other's kernels.  Sixteen host threads with a codec object (= a stream) each reached 2300 single-frame round
+// trips/s on device-resident data with the default and 3570 with 32 queues (profiles/r1_notes.md).  The variable is read
+// when the CUDA context is created, so this only helps when the library is loaded before that; a value the user set wins.
+const int g_connections_set = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+
 std::atomic<int> g_borrowed{0};           // engines that codec objects hold right now
 constexpr int blocking_sync_threshold = 6; // see Engine::wait_for
 } // namespace
@@ -154,6 +213,49 @@ int32_t Engine::wait_for(CUstream_st* stream)
     JLS_CUDA(cudaEventRecord(sleep_event_, stream));
     JLS_CUDA(cudaEventSynchronize(sleep_event_));
     return 0;
+}
+
+void Engine::trace_gpu(int index) noexcept
+{
+    if (!g_trace.enabled)
+        return;
+    if (!trace_events_[index])
+        cudaEventCreate(&trace_events_[index]);
+    cudaEventRecord(trace_events_[index], stream_);
+}
+
+void Engine::trace_host(int index) noexcept
+{
+    if (g_trace.enabled)
+        trace_host_ms_[index] = g_trace.now();
+}
+
+void Engine::trace_commit(int kind) noexcept
+{
+    if (!g_trace.enabled)
+        return;
+    std::lock_guard<std::mutex> lock(g_trace.mutex);
+    if (!g_trace.base)
+    {
+        // the base event goes first on the timeline: it is recorded before this call's events are read, on the
+        // legacy-free stream of this engine, and everything already recorded is measured against it (negative is fine)
+        cudaEventCreate(&g_trace.base);
+        cudaEventRecord(g_trace.base, stream_);
+        cudaEventSynchronize(g_trace.base);
+    }
+    TraceRecord r{};
+    r.thread = std::hash<std::thread::id>{}(std::this_thread::get_id()) % 100000;
+    r.kind = kind;
+    for (int i = 0; i < 4; ++i)
+    {
+        r.host_ms[i] = trace_host_ms_[i];
+        if (!trace_events_[i] || cudaEventElapsedTime(&r.gpu_ms[i], g_trace.base, trace_events_[i]) != cudaSuccess)
+        {
+            cudaGetLastError();
+            r.gpu_ms[i] = -1.0F;
+        }
+    }
+    g_trace.records.push_back(r);
 }
 
 void Engine::read_coder_time() noexcept
@@ -336,6 +438,8 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
 {
     written = 0;
     JLS_CHECK(prepare());
+    trace_host(0);
+    trace_gpu(0);
     const uint64_t launches_before = thread_kernel_launch_count();
     const size_t row_bytes = row_bytes_of(p);
     const size_t pitch = align_up(row_bytes, 16);
@@ -346,6 +450,7 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     else
         JLS_CUDA(cudaMemcpy2DAsync(pixels_.data, pitch, source, stride, row_bytes, static_cast<size_t>(p.height),
                                    cudaMemcpyHostToDevice, stream_));
+    trace_gpu(1);
 
     const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
     if (slot_bytes >= (size_t{1} << 32))
@@ -373,7 +478,10 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
                                  stream_));
         return 0;
     }));
+    trace_gpu(2);
+    trace_host(1);
     JLS_CHECK(wait_for(stream_));
+    trace_host(2);
     last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
     last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
@@ -386,8 +494,11 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     if (total != 0)
     {
         JLS_CUDA(cudaMemcpyAsync(destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
+        trace_gpu(3);
         JLS_CHECK(wait_for(stream_));
     }
+    trace_host(3);
+    trace_commit(0);
     written = static_cast<size_t>(total);
     return 0;
 }
@@ -395,8 +506,11 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
 int32_t Engine::upload_stream(const uint8_t* host_stream, size_t size)
 {
     JLS_CHECK(prepare());
+    trace_host(0);
+    trace_gpu(0);
     JLS_CHECK(ensure(stream_buffer_, size + 64));
     JLS_CUDA(cudaMemcpyAsync(stream_buffer_.data, host_stream, size, cudaMemcpyHostToDevice, stream_));
+    trace_gpu(1);
     uploaded_stream_size_ = size;
     return 0;
 }
@@ -441,7 +555,10 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
                                  stream_));
         return 0;
     }));
+    trace_gpu(2);
+    trace_host(1);
     JLS_CHECK(wait_for(stream_));
+    trace_host(2);
     last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
     last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
@@ -451,7 +568,10 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     consumed = static_cast<size_t>(outcome[1]);
     JLS_CUDA(cudaMemcpy2DAsync(destination, stride, pixels_.data, pitch, row_bytes, static_cast<size_t>(p.height),
                                cudaMemcpyDeviceToHost, stream_));
+    trace_gpu(3);
     JLS_CHECK(wait_for(stream_));
+    trace_host(3);
+    trace_commit(1);
     return 0;
 }
 

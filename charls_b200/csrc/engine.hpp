@@ -126,6 +126,12 @@ private:
     CUevent_st* events_[2]{};
     CUevent_st* sleep_event_{};
     std::vector<CachedGraph> graphs_;
+    // CHARLS_B200_TRACE timeline of the single-image calls (engine.cu: Trace)
+    void trace_gpu(int index) noexcept;
+    void trace_host(int index) noexcept;
+    void trace_commit(int kind) noexcept;
+    CUevent_st* trace_events_[4]{};
+    double trace_host_ms_[4]{};
     uint64_t buffer_generation_{};
 };
 

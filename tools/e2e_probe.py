@@ -66,6 +66,9 @@ for threads in ([int(t) for t in sys.argv[2].split(',')] if len(sys.argv) > 2 el
           f"enc call {sum(t_enc) / n * 1e3:6.2f} ms  dec call {sum(t_dec) / n * 1e3:6.2f} ms  ratio {w * h / (sum(sizes) / n):.2f}")
 assert torch.equal(out_host, frames_host)
 
+if len(sys.argv) > 3 and sys.argv[3] == "python-only":
+    sys.exit(0)
+
 # ---- the same round trips from C++ threads (charls_b200/csrc/driver): no interpreter lock between the ABI calls
 from charls_b200 import driver  # noqa: E402
 

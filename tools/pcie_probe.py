@@ -42,3 +42,28 @@ def both():
 
 t_h2d, t_d2h, t_both = timed(h2d), timed(d2h), timed(both)
 print(json.dumps({"h2d_gbs": n / t_h2d / 1e9, "d2h_gbs": n / t_d2h / 1e9, "bidirectional_sum_gbs": 2 * n / t_both / 1e9}))
+
+# ---- the copy pattern of the end-to-end bench without any kernel: 16 streams, per round trip 16.8 MB up, 8.4 MB down,
+# 8.4 MB up, 16.8 MB down (cfg2 frame and its stream), all asynchronous
+frame, comp = 4096 * 4096, 4096 * 4096 // 2
+streams = [torch.cuda.Stream() for _ in range(16)]
+hosts = [torch.empty(frame, dtype=torch.uint8).pin_memory() for _ in range(16)]
+devs = [torch.empty(frame, dtype=torch.uint8, device="cuda") for _ in range(16)]
+
+
+def pattern(sync_each):
+    for k, s in enumerate(streams):
+        with torch.cuda.stream(s):
+            devs[k].copy_(hosts[k], non_blocking=True)
+            hosts[k][:comp].copy_(devs[k][:comp], non_blocking=True)
+            if sync_each:
+                s.synchronize()
+            devs[k][:comp].copy_(hosts[k][:comp], non_blocking=True)
+            hosts[k].copy_(devs[k], non_blocking=True)
+
+
+for sync_each in (False,):
+    t = timed(lambda: pattern(sync_each), reps=4)
+    per_direction = 16 * (frame + comp) / t / 1e9
+    print(json.dumps({"pattern": "16 streams x (16.8 MB up, 8.4 MB down, 8.4 MB up, 16.8 MB down)", "each_direction_gbs": per_direction,
+                      "round_trips_per_s": 16 / t}))
