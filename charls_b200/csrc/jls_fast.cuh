@@ -275,7 +275,8 @@ struct FastWriter
         const int32_t length = high + 1 + k;
         if (JLS_LIKELY(high < escape && length <= 32))
         {
-            put<DEFERRED>((1U << k) | (static_cast<uint32_t>(mapped) & ((1U << k) - 1U)), length);
+            // mapped = high << k | low and the code word is 1 << k | low: flip the bits in which high differs from 1
+            put<DEFERRED>(static_cast<uint32_t>(mapped) ^ (static_cast<uint32_t>(high ^ 1) << k), length);
             return;
         }
         // long code word (more than 32 bits) or escape code: unary part in at most two pieces, then the binary part

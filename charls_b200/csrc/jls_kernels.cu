@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int warps = fast_block_threads / 32;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][2][32 * SW];
-    __shared__ uint8_t context_lut[context_lut_capacity];
+    extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
     const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
     for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, false>::pixels_per_top_up;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
-    __shared__ uint8_t context_lut[context_lut_capacity];
+    extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
     const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
     for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
@@ -246,22 +246,11 @@ __global__ void __launch_bounds__(fast_block_threads)
             // the pixels left in the line are needed on the rare run-mode path only
             const int32_t beyond = max(width - x0 - pixels_per_tile, 0); // pixels of the line after this tile
             int32_t n = width - x0 - beyond;
-#if defined(JLS_AB_DEC_PTR_LOOP)
-            S* const tile_end = sample + n * NC;
-            for (; sample != tile_end;)
-            {
-                const int32_t left = beyond + static_cast<int32_t>(tile_end - sample) / NC;
-                if (NC == 1 ? (reinterpret_cast<uintptr_t>(sample) & (refill_cadence * sizeof(S) - 1)) == 0
-                            : (left & (refill_cadence - 1)) == 0)
-                    dec.top_up();
-                dec.pixel(h, left);
-#else
             do
             {
                 if ((n & (refill_cadence - 1)) == 0)
                     dec.top_up();
                 dec.pixel(h, beyond + n);
-#endif
                 int32_t v[NC];
 #pragma unroll
                 for (int32_t c = 0; c < NC; ++c)
@@ -272,11 +261,7 @@ __global__ void __launch_bounds__(fast_block_threads)
                 for (int32_t c = 0; c < NC; ++c)
                     sample[c] = static_cast<S>(v[c]);
                 sample += NC;
-#if defined(JLS_AB_DEC_PTR_LOOP)
-            }
-#else
             } while (--n != 0);
-#endif
         }
         __syncwarp();
         tile_store<TW>(tile, pixels, stride, first_line, row_mask, row_bytes, t, lane);
@@ -677,6 +662,23 @@ cudaError_t launch(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, Ar
     return cudaGetLastError();
 }
 
+template<typename Kernel, typename... Args>
+cudaError_t launch_with_shared(Kernel kernel, dim3 grid, dim3 block, size_t dynamic_shared_bytes, cudaStream_t stream, Args... args)
+{
+    kernel<<<grid, block, dynamic_shared_bytes, stream>>>(args...);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    ++t_kernel_launches;
+    return cudaGetLastError();
+}
+
+// The tile kernels keep the context-index table |Q(-Ra)|, Ra = 0 .. min(T3, capacity - 1), in dynamic shared memory: 22
+// bytes for 8-bit defaults, 277 for 12..16 bit.  A fixed 1 KB table per one-warp block costs three resident blocks per SM.
+size_t tiled_dynamic_shared_bytes(const CodecParams& p)
+{
+    const size_t entries = static_cast<size_t>(p.t3 < context_lut_capacity - 1 ? p.t3 : context_lut_capacity - 1) + 1;
+    return (entries + 15) / 16 * 16;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Variant selection for the fast path -- the counterpart of the reference's make_scan_codec (src/make_scan_codec.cpp:40-156):
 // components per pixel (1 = scalar lines, 2..4 = sample interleave), lossless or not, 8 / 16 bit containers,
@@ -694,7 +696,7 @@ cudaError_t launch_encode_fast(const CodecParams& p, bool tiled, dim3 grid, dim3
                                const ScanJob* jobs, size_t slot_bytes)
 {
     if (tiled)
-        return launch(k_encode_tiled<NC, LL, S>, grid, block, stream, p, jobs, slot_bytes);
+        return launch_with_shared(k_encode_tiled<NC, LL, S>, grid, block, tiled_dynamic_shared_bytes(p), stream, p, jobs, slot_bytes);
     if constexpr (NC == 1)
     {
         if (p.interleave == ilv_line)
@@ -707,7 +709,7 @@ template<int NC, bool LL, typename S>
 cudaError_t launch_decode_fast(const CodecParams& p, bool tiled, dim3 grid, dim3 block, cudaStream_t stream, const ScanJob* jobs)
 {
     if (tiled)
-        return launch(k_decode_tiled<NC, LL, S>, grid, block, stream, p, jobs);
+        return launch_with_shared(k_decode_tiled<NC, LL, S>, grid, block, tiled_dynamic_shared_bytes(p), stream, p, jobs);
     if constexpr (NC == 1)
     {
         if (p.interleave == ilv_line)
