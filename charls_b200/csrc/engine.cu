@@ -531,7 +531,7 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
     // size share one captured graph
     const size_t grid_bytes = align_up(remaining + 1, size_t{1} << 20);
     const size_t blocks = marker_blocks_for(grid_bytes);
-    JLS_CHECK(ensure(marker_counts_, (blocks + 1) * sizeof(uint32_t)));
+    JLS_CHECK(ensure(marker_counts_, marker_scratch_bytes(1, grid_bytes)));
     JLS_CHECK(ensure(marker_totals_, sizeof(uint32_t)));
     JLS_CHECK(ensure(marker_codes_, p.interval_count));
 
@@ -683,8 +683,7 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
         job.stream_in_size = frames[i].stream_capacity - frames[i].scan_offset;
         max_remaining = job.stream_in_size > max_remaining ? job.stream_in_size : max_remaining;
     }
-    const size_t blocks = marker_blocks_for(max_remaining);
-    JLS_CHECK(ensure(marker_counts_, count * (blocks + 1) * sizeof(uint32_t)));
+    JLS_CHECK(ensure(marker_counts_, marker_scratch_bytes(count, max_remaining)));
     JLS_CHECK(ensure(marker_totals_, count * sizeof(uint32_t)));
     JLS_CHECK(ensure(marker_codes_, count * p.interval_count));
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream));

@@ -440,11 +440,16 @@ struct MarkerChunk
     int64_t base;
 };
 
-__device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t size, size_t chunk_index)
+__device__ __forceinline__ int64_t marker_chunk_base(const uint8_t* data, size_t chunk_index)
 {
     const int64_t lead = static_cast<int64_t>(reinterpret_cast<uintptr_t>(data) & 15U);
+    return static_cast<int64_t>(chunk_index) * marker_bytes_per_thread - lead;
+}
+
+__device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t size, size_t chunk_index)
+{
     MarkerChunk chunk;
-    chunk.base = static_cast<int64_t>(chunk_index) * marker_bytes_per_thread - lead;
+    chunk.base = marker_chunk_base(data, chunk_index);
     chunk.mask = 0;
     const int64_t n = static_cast<int64_t>(size);
     if (chunk.base >= n)
@@ -480,11 +485,15 @@ __device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t 
 
 // grid (blocks, jobs): block_counts[job][block]
 __global__ void __launch_bounds__(marker_block_threads)
-    k_marker_count(const ScanJob* __restrict__ jobs, uint32_t* __restrict__ block_counts, uint32_t blocks_per_job)
+    k_marker_count(const ScanJob* __restrict__ jobs, uint32_t* __restrict__ block_counts, uint32_t blocks_per_job,
+                   uint16_t* __restrict__ chunk_masks)
 {
     const ScanJob& job = jobs[blockIdx.y];
     const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
-    const uint32_t count = __popc(marker_chunk(job.stream_in, job.stream_in_size, chunk_index).mask);
+    const uint32_t mask = marker_chunk(job.stream_in, job.stream_in_size, chunk_index).mask;
+    // kept for k_marker_write: 2 bytes per 16 stream bytes instead of a second pass over the stream
+    chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index] = static_cast<uint16_t>(mask);
+    const uint32_t count = __popc(mask);
     __shared__ uint32_t warp_sums[marker_block_threads / 32];
     uint32_t sum = count;
 #pragma unroll
@@ -527,12 +536,15 @@ __global__ void __launch_bounds__(scan_block_threads)
 // each marker's code in marker_codes[job][i].
 __global__ void __launch_bounds__(marker_block_threads)
     k_marker_write(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
-                   const uint32_t* __restrict__ block_counts, uint32_t blocks_per_job, uint8_t* __restrict__ marker_codes)
+                   const uint32_t* __restrict__ block_counts, uint32_t blocks_per_job, uint8_t* __restrict__ marker_codes,
+                   const uint16_t* __restrict__ chunk_masks)
 {
     __shared__ uint32_t warp_sums[marker_block_threads / 32];
     const ScanJob& job = jobs[blockIdx.y];
     const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
-    const MarkerChunk chunk = marker_chunk(job.stream_in, job.stream_in_size, chunk_index);
+    MarkerChunk chunk;
+    chunk.base = marker_chunk_base(job.stream_in, chunk_index);
+    chunk.mask = chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index];
     const uint32_t mask = chunk.mask;
     const uint32_t count = __popc(mask);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -799,6 +811,19 @@ size_t marker_blocks_for(size_t stream_bytes) noexcept
     return (stream_bytes + 15 + marker_bytes_per_block - 1) / marker_bytes_per_block;
 }
 
+// Layout of the marker scratch: [jobs][blocks] uint32 block counts (rounded up to 16 bytes), then [jobs][blocks][threads]
+// uint16 chunk masks.
+static size_t marker_counts_bytes(size_t job_count, size_t blocks_per_job) noexcept
+{
+    return (job_count * blocks_per_job * sizeof(uint32_t) + 15) / 16 * 16;
+}
+
+size_t marker_scratch_bytes(size_t job_count, size_t max_stream_bytes) noexcept
+{
+    const size_t blocks = marker_blocks_for(max_stream_bytes);
+    return marker_counts_bytes(job_count, blocks) + job_count * blocks * marker_block_threads * sizeof(uint16_t);
+}
+
 #define JLS_TRY(expr)                                                                                                  \
     do                                                                                                                 \
     {                                                                                                                  \
@@ -844,12 +869,15 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
     JLS_TRY(launch(k_init_decode_tables, dim3((2 * p.interval_count + 255) / 256, job_count), dim3(256), stream, p,
                    device_jobs));
+    uint16_t* chunk_masks =
+        reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(block_counts) + marker_counts_bytes(job_count, blocks_per_job));
     JLS_TRY(launch(k_marker_count, dim3(blocks_per_job, job_count), dim3(marker_block_threads), stream, device_jobs,
-                   block_counts, blocks_per_job));
+                   block_counts, blocks_per_job, chunk_masks));
     JLS_TRY(launch(k_marker_scan, dim3(job_count), dim3(scan_block_threads), stream, block_counts, blocks_per_job,
                    marker_totals));
     JLS_TRY(launch(k_marker_write, dim3(blocks_per_job, job_count), dim3(marker_block_threads), stream, p, device_jobs,
-                   static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes));
+                   static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes,
+                   static_cast<const uint16_t*>(chunk_masks)));
 
     const bool lossless = p.near == 0;
     if (coder_events)

@@ -16,6 +16,7 @@ void count_kernel_launches(uint32_t launches) noexcept;
 
 // Blocks (of 4096 stream bytes) the marker kernels use for a stream of `stream_bytes`.
 size_t marker_blocks_for(size_t stream_bytes) noexcept;
+size_t marker_scratch_bytes(size_t job_count, size_t max_stream_bytes) noexcept;
 
 // Encodes `job_count` scans that share the coding parameters `p`.  Afterwards, per job: result[0] = bytes written to
 // stream_out (interval data + RSTm markers), status = first error key (~0 when none).
@@ -24,8 +25,9 @@ size_t marker_blocks_for(size_t stream_bytes) noexcept;
 cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
                           cudaStream_t stream, cudaEvent_t* coder_events = nullptr, bool rows_word_aligned = false);
 
-// Decodes `job_count` scans.  block_counts: job_count * marker_blocks_for(max_stream_bytes) uint32; marker_totals:
-// job_count uint32; marker_codes: job_count * interval_count bytes.  Afterwards result[0] = bytes consumed by the scan.
+// Decodes `job_count` scans.  block_counts: marker_scratch_bytes(job_count, max_stream_bytes) bytes of scratch (block
+// counts, then the per-chunk marker masks); marker_totals: job_count uint32; marker_codes: job_count * interval_count
+// bytes.  Afterwards result[0] = bytes consumed by the scan.
 cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
                           uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream,
                           cudaEvent_t* coder_events = nullptr, bool rows_word_aligned = false);
