@@ -121,6 +121,7 @@ struct charls_jpegls_decoder final
         check_buffer(destination, destination_size);
         check_operation(state_ == State::header_read);
         const charls_frame_info& info = reader_.frame_info();
+        (void)check_stride_and_destination_size(destination_size, stride); // argument errors come before any device work
         check_status(engine().upload_stream(reader_.source_data(), reader_.source_size()));
 
         for (size_t component = 0;;)

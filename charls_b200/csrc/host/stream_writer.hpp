@@ -17,14 +17,15 @@ class StreamWriter final
 public:
     void destination(uint8_t* data, size_t size) noexcept
     {
+        // the write position survives, as in the reference (src/jpeg_stream_writer.hpp:129-132): a segment that did not
+        // fit leaves the bytes written before it counted, whatever buffer is set next; only rewind() starts over
         data_ = data;
         size_ = size;
-        position_ = 0;
     }
 
     size_t bytes_written() const noexcept { return position_; }
     uint8_t* remaining_data() const noexcept { return data_ + position_; }
-    size_t remaining_size() const noexcept { return size_ - position_; }
+    size_t remaining_size() const noexcept { return position_ < size_ ? size_ - position_ : 0; }
     void advance(size_t count) noexcept { position_ += count; }
 
     void rewind() noexcept
