@@ -330,3 +330,39 @@ def test_cpp_driver_round_trips(product):
         assert seconds > 0 and np.array_equal(out, frames)
         for i in range(n):
             assert streams[i, : sizes[i]].tobytes() == encode(product, frames[i], 8)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_parameters_vs_oracle(product, oracle, seed):
+    """Seeded random walk over the parameter space through the real kernels (tests/test_hostemu.py does the same walk on
+    the host-compiled kernel code): widths around the 64-byte tile edges, every bit depth, NEAR up to its limit, presets,
+    all interleave modes, colour transforms, restart intervals."""
+    import random
+
+    rng = random.Random(7000 + seed)
+    for _ in range(30):
+        bits = rng.choice([2, 3, 5, 7, 8, 8, 9, 10, 12, 12, 15, 16, 16])
+        maxval = (1 << bits) - 1
+        cc = rng.choice([1, 1, 1, 2, 3, 3, 4])
+        ilv = 0 if cc == 1 else rng.choice([0, 1, 2])
+        near = min(rng.choice([0, 0, 0, 1, 2, 3, 255]), maxval // 2, 255)
+        xf = rng.choice([0, 1, 2, 3]) if (cc == 3 and ilv != 0 and near == 0 and bits in (8, 16)) else 0
+        ri = rng.choice([1, 1, 1, 0, 2, 5])
+        w, h = rng.choice([1, 3, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200, 1023]), rng.choice([1, 2, 31, 32, 33, 70])
+        preset = None
+        if rng.random() < 0.35:
+            t1 = rng.randint(near + 1, maxval)
+            t2 = rng.randint(t1, maxval)
+            t3 = rng.randint(t2, maxval)
+            preset = (0, t1, t2, t3, rng.choice([3, 4, 31, 64, 255]))
+        gen = rng.choice([s_smooth, s_noise, s_mixed])
+        layout = "planar" if ilv == 0 else "interleaved"
+        img = gen(h, w, bits, cc, seed=rng.randrange(1 << 30), layout=layout) if cc > 1 else gen(h, w, bits, seed=rng.randrange(1 << 30))
+        case = (bits, cc, ilv, near, xf, ri, w, h, preset, gen.__name__)
+        got = encode(product, img, bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=ri,
+                     preset=preset)
+        want = oracle.encode_image(img, bits, near=near, ilv=ilv, xform=xf, pc=preset, ri=ri)
+        assert payloads(got) == payloads(want), case
+        expected, _ = oracle.decode_image(got)
+        px, _, _ = codec.decode(got, lib=product)
+        assert np.array_equal(px, expected), case

@@ -90,3 +90,31 @@ def test_golden_vectors(oracle, hostemu, golden):
         out = np.zeros_like(v.image)
         assert hostemu.decode(hp, want + b"\xff\xd9", out) == len(want), v.name
         assert np.array_equal(out, v.dec1), v.name
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_parameters(oracle, hostemu, seed):
+    """Seeded random walk over the parameter space (bit depth, NEAR up to its limit, presets, component counts,
+    interleave modes, colour transforms, restart intervals, odd sizes): kernel code == oracle, byte for byte."""
+    import random
+
+    rng = random.Random(4000 + seed)
+    for _ in range(40):
+        bits = rng.choice([2, 3, 5, 7, 8, 8, 9, 10, 12, 12, 15, 16, 16])
+        maxval = (1 << bits) - 1
+        cc = rng.choice([1, 1, 1, 2, 3, 3, 4])
+        ilv = 0 if cc == 1 else rng.choice([1, 2])
+        near = rng.choice([0, 0, 0, 1, 2, 3, min(255, maxval // 2)])
+        near = min(near, maxval // 2, 255)
+        xf = rng.choice([0, 1, 2, 3]) if (cc == 3 and near == 0 and bits in (8, 16)) else 0
+        ri = rng.choice([1, 1, 1, 0, 2, 5])
+        w, h = rng.choice([1, 2, 3, 17, 64, 65, 127, 200, 301]), rng.choice([1, 2, 5, 9])
+        pc = None
+        if rng.random() < 0.35:
+            t1 = rng.randint(near + 1, maxval)
+            t2 = rng.randint(t1, maxval)
+            t3 = rng.randint(t2, maxval)
+            pc = (0, t1, t2, t3, rng.choice([3, 4, 31, 64, 255]))
+        gen = rng.choice([s_smooth, s_noise, s_mixed])
+        img = gen(h, w, bits, cc, seed=rng.randrange(1 << 30), layout="interleaved") if cc > 1 else gen(h, w, bits, seed=rng.randrange(1 << 30))
+        check_scan(oracle, hostemu, img, bits, cc, near, ilv, xf, ri, pc)
