@@ -51,15 +51,29 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-phases", action="store_true", help="e2e: encode all frames, then decode all (default: per frame)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--content", default="smooth", choices=["smooth", "noise", "flat"],
+                    help="smooth = S_smooth (the metric's input); noise (uniform, incompressible) and flat (all zero, pure run "
+                         "mode) bracket it (SURVEY.md 8d)")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # synthetic frames: S_smooth of SURVEY.md 8(d) -- smooth base + 1% gaussian noise, generated on the device
 # ---------------------------------------------------------------------------------------------------------------------
-def make_frames(torch, device, count, workload, first_seed):
+def make_frames(torch, device, count, workload, first_seed, content="smooth"):
     w, h, bits, cc, _, ilv, _ = WORKLOADS[workload]
     mx = (1 << bits) - 1
+    if content != "smooth":
+        dtype = torch.uint8 if bits <= 8 else torch.int16
+        shape = (count, h, w) if cc == 1 else (count, h, w, cc)
+        if content == "flat":
+            return torch.zeros(shape, device=device, dtype=dtype)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(first_seed)
+        v = torch.randint(0, mx + 1, shape, device=device, generator=gen, dtype=torch.int32)
+        if bits > 8:
+            v = torch.where(v > 32767, v - 65536, v)
+        return v.to(dtype)
     x = torch.arange(w, device=device, dtype=torch.float32)[None, :]
     y = torch.arange(h, device=device, dtype=torch.float32)[:, None]
     base = 0.8 * mx * (0.5 + 0.25 * torch.sin(x / 97.0) + 0.25 * torch.cos(y / 131.0))
@@ -240,8 +254,9 @@ def run_reference_arm(args):
 
 def workload_name(args):
     w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
+    content = "" if args.content == "smooth" else f", content={args.content}"
     return (f"{args.workload}: {w}x{h} {bits}-bit x{cc} NEAR={near} ILV={ilv} HP{xf} restart-interval=1, "
-            f"{args.frames} frames per GPU per step")
+            f"{args.frames} frames per GPU per step{content}")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -315,8 +330,10 @@ def run_gpu_arm(args):
     lib.check(lib.charlsx_set_device(local_rank))
     w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
     F = args.frames
-    frames = make_frames(torch, device, F, args.workload, first_seed=1234 + rank * F)
+    frames = make_frames(torch, device, F, args.workload, first_seed=1234 + rank * F, content=args.content)
     codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=1, lib=lib)
+    if args.content == "noise":
+        codec.stream_capacity *= 2  # incompressible input expands (about 9.5 bits per 8-bit sample)
     streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
     decoded = torch.empty_like(frames)
     raw_bytes = frames[0].numel() * frames.element_size()
