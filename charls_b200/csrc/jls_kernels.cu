@@ -392,6 +392,8 @@ __global__ void __launch_bounds__(gather_block_threads)
     const uint32_t bytes = job.interval_bytes[interval];
     const uint8_t* source = job.slots + static_cast<size_t>(interval) * slot_bytes;
     uint8_t* destination = job.stream_out + job.interval_offset[interval];
+    assume_global(source);
+    assume_global(destination);
 
     // head: bytes until the destination is 4-byte aligned; body: aligned 32-bit stores fed by two aligned loads and a
     // funnel shift; tail: bytes
@@ -402,11 +404,24 @@ __global__ void __launch_bounds__(gather_block_threads)
     const uint32_t* source_words = reinterpret_cast<const uint32_t*>(source + (head & ~3U)); // slots are 16-byte aligned
     const uint32_t shift = (head & 3U) * 8U;
     uint32_t* destination_words = reinterpret_cast<uint32_t*>(destination + head);
-    for (uint32_t w = lane; w < body_words; w += 32)
+    // four independent word copies per lane and iteration: the loads of one iteration are in flight together
+    for (uint32_t w = lane; w < body_words; w += 128)
     {
-        const uint32_t lo = source_words[w];
-        const uint32_t hi = shift ? source_words[w + 1] : 0U;
-        destination_words[w] = __funnelshift_r(lo, hi, shift);
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i)
+        {
+            const uint32_t index = w + 32U * i;
+            lo[i] = index < body_words ? source_words[index] : 0U;
+            hi[i] = (shift != 0 && index < body_words) ? source_words[index + 1] : 0U;
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i)
+        {
+            const uint32_t index = w + 32U * i;
+            if (index < body_words)
+                destination_words[index] = __funnelshift_r(lo[i], hi[i], shift);
+        }
     }
     const uint32_t done = head + body_words * 4U;
     if (lane < bytes - done)
@@ -448,6 +463,7 @@ __device__ __forceinline__ int64_t marker_chunk_base(const uint8_t* data, size_t
 
 __device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t size, size_t chunk_index)
 {
+    assume_global(data);
     MarkerChunk chunk;
     chunk.base = marker_chunk_base(data, chunk_index);
     chunk.mask = 0;
@@ -542,6 +558,7 @@ __global__ void __launch_bounds__(marker_block_threads)
     __shared__ uint32_t warp_sums[marker_block_threads / 32];
     const ScanJob& job = jobs[blockIdx.y];
     const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
+    assume_global(job.stream_in);
     MarkerChunk chunk;
     chunk.base = marker_chunk_base(job.stream_in, chunk_index);
     chunk.mask = chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index];
