@@ -273,7 +273,7 @@ struct FastWriter
     {
         const int32_t high = mapped >> k;
         const int32_t length = high + 1 + k;
-        if (JLS_LIKELY(high < escape && length <= 32))
+        if (JLS_LIKELY(high < imin(escape, 32 - k))) // no escape and length <= 32: one compare
         {
             // mapped = high << k | low and the code word is 1 << k | low: flip the bits in which high differs from 1
             put<DEFERRED>(static_cast<uint32_t>(mapped) ^ (static_cast<uint32_t>(high ^ 1) << k), length);

@@ -461,6 +461,23 @@ __device__ __forceinline__ int64_t marker_chunk_base(const uint8_t* data, size_t
     return static_cast<int64_t>(chunk_index) * marker_bytes_per_thread - lead;
 }
 
+// bit i <=> byte i of the 16 bytes in q is a marker code byte; `previous` = the stream byte in front of them
+__device__ __forceinline__ uint32_t marker_mask_of(const uint4& q, uint32_t previous)
+{
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        // byte j of `shifted` is the stream byte in front of byte j of w[i] (little endian: earlier byte = lower bits)
+        const uint32_t shifted = (w[i] << 8) | previous;
+        const uint32_t m = ff_bytes(shifted) & w[i] & ~ff_bytes(w[i]); // 0x80 where FF is followed by >= 0x80, != FF
+        mask |= (((m >> 7) & 1U) | ((m >> 14) & 2U) | ((m >> 21) & 4U) | ((m >> 28) & 8U)) << (4 * i);
+        previous = w[i] >> 24;
+    }
+    return mask;
+}
+
 __device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t size, size_t chunk_index)
 {
     assume_global(data);
@@ -473,17 +490,7 @@ __device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t 
     if (chunk.base >= 1 && chunk.base + marker_bytes_per_thread <= n)
     {
         const uint4 q = *reinterpret_cast<const uint4*>(data + chunk.base);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t previous = data[chunk.base - 1];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            // byte j of `shifted` is the stream byte in front of byte j of w[i] (little endian: earlier byte = lower bits)
-            const uint32_t shifted = (w[i] << 8) | previous;
-            const uint32_t m = ff_bytes(shifted) & w[i] & ~ff_bytes(w[i]); // 0x80 where FF is followed by >= 0x80, != FF
-            chunk.mask |= (((m >> 7) & 1U) | ((m >> 14) & 2U) | ((m >> 21) & 4U) | ((m >> 28) & 8U)) << (4 * i);
-            previous = w[i] >> 24;
-        }
+        chunk.mask = marker_mask_of(q, data[chunk.base - 1]);
         return chunk;
     }
     const int64_t begin = chunk.base < 0 ? 0 : chunk.base;
@@ -506,7 +513,24 @@ __global__ void __launch_bounds__(marker_block_threads)
 {
     const ScanJob& job = jobs[blockIdx.y];
     const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
-    const uint32_t mask = marker_chunk(job.stream_in, job.stream_in_size, chunk_index).mask;
+    uint32_t mask;
+    const int64_t base = marker_chunk_base(job.stream_in, chunk_index);
+    const bool interior = base >= 1 && base + marker_bytes_per_thread <= static_cast<int64_t>(job.stream_in_size);
+    if (__all_sync(0xFFFFFFFFU, interior))
+    {
+        // the whole warp reads 512 consecutive stream bytes: a lane's preceding byte is its neighbour's last one
+        const uint8_t* data = job.stream_in;
+        assume_global(data);
+        const uint4 q = *reinterpret_cast<const uint4*>(data + base);
+        uint32_t previous = __shfl_up_sync(0xFFFFFFFFU, q.w >> 24, 1);
+        if ((threadIdx.x & 31) == 0)
+            previous = data[base - 1];
+        mask = marker_mask_of(q, previous);
+    }
+    else
+    {
+        mask = marker_chunk(job.stream_in, job.stream_in_size, chunk_index).mask;
+    }
     // kept for k_marker_write: 2 bytes per 16 stream bytes instead of a second pass over the stream
     chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index] = static_cast<uint16_t>(mask);
     const uint32_t count = __popc(mask);
