@@ -431,6 +431,30 @@ def run_gpu_arm(args):
             "api": "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
         }
 
+        # ---- the same host buffers through the host-batch extension: one call per direction from one host thread, the
+        # library stages chunks of frames and overlaps their copies with the kernels (reported beside e2e, not as e2e:
+        # the reference's interface has no multi-image call)
+        pixels_in = [frames_host[i] for i in range(n)]
+        streams_io = [streams_host[i] for i in range(n)]
+        pixels_out = [out_host[i] for i in range(n)]
+        t_batch = 0.0
+        for rep in range(2 + reps):
+            out_host.zero_()
+            t0 = time.perf_counter()
+            batch_sizes = codec.encode_host(pixels_in, streams_io)
+            codec.decode_host(streams_io, batch_sizes, pixels_out)
+            if rep >= 2:
+                t_batch += time.perf_counter() - t0
+        if near == 0:
+            assert torch.equal(out_host, frames_host), "host-batch round trip mismatch"
+        tb = torch.tensor([t_batch / reps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        e2e["host_batch"] = {
+            "value": world * n * w * h / float(tb.item()) / 1e6, "unit": "MPixels/s", "host_threads": 1,
+            "api": "charlsx_batch_encode_host, then charlsx_batch_decode_host (extension), same pinned host buffers",
+        }
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -71,6 +71,30 @@ class BatchCodec:
         self.lib.check(errc)
         return [images[i].stream_size for i in range(len(images))]
 
+    # ---- frames and streams in host memory (numpy arrays or pinned torch tensors); see charlsx_batch_encode_host
+    @staticmethod
+    def _host_images(pixels, streams, sizes):
+        n = len(pixels)
+        images = (BatchImage * n)()
+        for i in range(n):
+            images[i].pixels = pixels[i].ctypes.data if hasattr(pixels[i], "ctypes") else pixels[i].data_ptr()
+            images[i].stream = streams[i].ctypes.data if hasattr(streams[i], "ctypes") else streams[i].data_ptr()
+            capacity = streams[i].nbytes if hasattr(streams[i], "nbytes") else streams[i].numel() * streams[i].element_size()
+            images[i].stream_capacity = capacity if sizes is None else int(sizes[i])
+        return images
+
+    def encode_host(self, pixels, streams):
+        """pixels[i], streams[i]: host arrays (frame i, its stream buffer).  Returns the list of stream sizes."""
+        images = self._host_images(pixels, streams, None)
+        self.lib.check(self.lib.charlsx_batch_encode_host(self._h, byref(self.params), images, len(images)))
+        return [images[i].stream_size for i in range(len(images))]
+
+    def decode_host(self, streams, sizes, pixels):
+        """streams[i]: host array with a complete JPEG-LS stream of sizes[i] bytes; pixels[i]: host output array."""
+        images = self._host_images(pixels, streams, sizes)
+        self.lib.check(self.lib.charlsx_batch_decode_host(self._h, byref(self.params), images, len(images)))
+        return [images[i].stream_size for i in range(len(images))]
+
     def last_coder_kernel_ms(self) -> float:
         ms = C.c_float()
         self.lib.check(self.lib.charlsx_batch_get_last_coder_kernel_ms(self._h, byref(ms)))

@@ -157,6 +157,8 @@ EXT_SYMBOLS = {
     "charlsx_batch_destroy": (None, [c_void_p]),
     "charlsx_batch_encode": (_ERR, [c_void_p, POINTER(BatchParams), POINTER(BatchImage), c_size_t, c_void_p]),
     "charlsx_batch_decode": (_ERR, [c_void_p, POINTER(BatchParams), POINTER(BatchImage), c_size_t, c_void_p]),
+    "charlsx_batch_encode_host": (_ERR, [c_void_p, POINTER(BatchParams), POINTER(BatchImage), c_size_t]),
+    "charlsx_batch_decode_host": (_ERR, [c_void_p, POINTER(BatchParams), POINTER(BatchImage), c_size_t]),
     "charlsx_batch_get_last_kernel_launches": (_ERR, [c_void_p, POINTER(c_uint32)]),
     "charlsx_batch_get_last_coder_kernel_ms": (_ERR, [c_void_p, POINTER(C.c_float)]),
     "charlsx_get_kernel_launch_count": (_ERR, [POINTER(C.c_uint64)]),

@@ -92,6 +92,18 @@ Engine::~Engine()
         if (event)
             cudaEventDestroy(event);
     drop_graphs();
+    for (Buffer* b : {&stage_pixels_[0], &stage_pixels_[1], &stage_streams_[0], &stage_streams_[1]})
+        release(*b);
+    for (auto& event : in_done_)
+        if (event)
+            cudaEventDestroy(event);
+    for (auto& event : out_done_)
+        if (event)
+            cudaEventDestroy(event);
+    if (copy_in_)
+        cudaStreamDestroy(copy_in_);
+    if (copy_out_)
+        cudaStreamDestroy(copy_out_);
     for (auto& event : trace_events_)
         if (event)
             cudaEventDestroy(event);
@@ -579,7 +591,7 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
 // Batch path: device-resident frames
 // ---------------------------------------------------------------------------------------------------------------------
 int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
-                             size_t stride, CUstream_st* user_stream)
+                             size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding)
 {
     JLS_CHECK(prepare());
     if (count == 0)
@@ -613,7 +625,12 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream, events_, word_aligned));
     JLS_CUDA(launch_wrap_frames(device_jobs, static_cast<const uint8_t*>(header_.data), static_cast<uint32_t>(header_size),
                                 static_cast<uint32_t>(count), stream));
-    JLS_CHECK(fetch_outcomes(count, stream));
+    JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
+    JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                             stream));
+    if (while_coding)
+        JLS_CHECK(while_coding());
+    JLS_CHECK(wait_for(stream));
     read_coder_time();
     last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 
@@ -630,6 +647,192 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
         if (status != 0 && first_error == 0)
             first_error = status;
     }
+    return first_error;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batch path: host-resident frames, staged through device memory chunk by chunk
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t Engine::prepare_staging()
+{
+    JLS_CHECK(prepare());
+    if (!copy_in_)
+        JLS_CUDA(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking));
+    if (!copy_out_)
+        JLS_CUDA(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking));
+    for (auto& event : in_done_)
+        if (!event)
+            JLS_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+    for (auto& event : out_done_)
+        if (!event)
+            JLS_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+    return 0;
+}
+
+// Frames per staging slot.  A chunk's kernels take at least the latency of one line (~1.3 ms for 4096 samples) however few
+// frames it holds, so chunks hold at least six frames (2 ms of PCIe time each way for 16 MB frames); beyond that smaller
+// chunks mean less time to fill and drain the pipeline (about eight chunks per call), and two slots stay below 512 MiB each.
+size_t Engine::staging_chunk(size_t count, size_t bytes_per_frame) noexcept
+{
+    constexpr size_t slot_budget = size_t{512} << 20;
+    size_t largest = slot_budget / (bytes_per_frame ? bytes_per_frame : 1);
+    largest = largest < 1 ? 1 : largest > 64 ? 64 : largest;
+    size_t chunk = (count + 7) / 8;
+    chunk = chunk < 6 ? 6 : chunk;
+    chunk = chunk > largest ? largest : chunk;
+    return chunk > count ? count : chunk;
+}
+
+int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
+                                  size_t stride)
+{
+    if (count == 0)
+        return 0;
+    JLS_CHECK(prepare_staging());
+    const size_t row_bytes = row_bytes_of(p);
+    const size_t frame_bytes = stride * (static_cast<size_t>(p.height) - 1) + row_bytes;
+    const size_t frame_pitch = align_up(stride * static_cast<size_t>(p.height), 256); // distance between staged frames
+    const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
+    size_t stream_slot = header_size + static_cast<size_t>(p.interval_count) * (slot_bytes + 2) + 2; // nothing is longer
+    size_t largest_capacity = 0;
+    for (size_t i = 0; i < count; ++i)
+        largest_capacity = frames[i].stream_capacity > largest_capacity ? frames[i].stream_capacity : largest_capacity;
+    stream_slot = align_up(stream_slot < largest_capacity ? stream_slot : largest_capacity, 256);
+    const size_t chunk = staging_chunk(count, frame_pitch + stream_slot);
+    for (int s = 0; s < 2; ++s)
+    {
+        JLS_CHECK(ensure(stage_pixels_[s], chunk * frame_pitch + 64));
+        JLS_CHECK(ensure(stage_streams_[s], chunk * stream_slot + 64));
+    }
+
+    const size_t chunks = (count + chunk - 1) / chunk;
+    std::vector<BatchFrame> staged(chunk);
+    const auto upload = [&](size_t j) -> int32_t {
+        const int s = static_cast<int>(j & 1U);
+        // the slot is free once the stream copies of the chunk that used it before have left it
+        JLS_CUDA(cudaStreamWaitEvent(copy_in_, out_done_[s], 0));
+        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+        for (size_t k = 0; k < n; ++k)
+            JLS_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch, frames[first + k].pixels, frame_bytes,
+                                     cudaMemcpyHostToDevice, copy_in_));
+        JLS_CUDA(cudaEventRecord(in_done_[s], copy_in_));
+        return 0;
+    };
+
+    int32_t first_error = 0;
+    JLS_CUDA(cudaEventRecord(out_done_[0], copy_out_)); // both slots start free
+    JLS_CUDA(cudaEventRecord(out_done_[1], copy_out_));
+    JLS_CHECK(upload(0));
+    uint32_t launches = 0;
+    for (size_t j = 0; j < chunks; ++j)
+    {
+        const int s = static_cast<int>(j & 1U);
+        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+        for (size_t k = 0; k < n; ++k)
+        {
+            const size_t capacity = frames[first + k].stream_capacity < stream_slot ? frames[first + k].stream_capacity : stream_slot;
+            staged[k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
+                                   static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, capacity, 0, 0, 0};
+        }
+        JLS_CUDA(cudaStreamWaitEvent(stream_, in_done_[s], 0));
+        const double t_before = g_trace.enabled ? g_trace.now() : 0.0;
+        // the next chunk's copies are issued behind this chunk's kernels: streams that share a hardware queue run in issue
+        // order, and a copy issued first would hold the kernels back
+        const int32_t status = encode_batch(p, header, header_size, staged.data(), n, stride, stream_,
+                                            [&]() -> int32_t { return j + 1 < chunks ? upload(j + 1) : 0; });
+        if (g_trace.enabled)
+            std::fprintf(stderr, "encode_batch_host chunk %zu/%zu (%zu frames): coded at %.3f ms, waited %.3f ms\n", j, chunks, n,
+                         g_trace.now(), g_trace.now() - t_before);
+        launches += last_launches_;
+        if (status != 0 && first_error == 0)
+            first_error = status;
+        for (size_t k = 0; k < n; ++k)
+        {
+            frames[first + k].status = staged[k].status;
+            frames[first + k].stream_size = staged[k].stream_size;
+            if (staged[k].status == 0)
+                JLS_CUDA(cudaMemcpyAsync(frames[first + k].stream, staged[k].stream, staged[k].stream_size, cudaMemcpyDeviceToHost,
+                                         copy_out_));
+        }
+        JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_));
+    }
+    const double t_drain = g_trace.enabled ? g_trace.now() : 0.0;
+    JLS_CHECK(wait_for(copy_out_));
+    if (g_trace.enabled)
+        std::fprintf(stderr, "encode_batch_host: drained at %.3f ms after %.3f ms\n", g_trace.now(), g_trace.now() - t_drain);
+    last_launches_ = launches;
+    return first_error;
+}
+
+int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride)
+{
+    if (count == 0)
+        return 0;
+    JLS_CHECK(prepare_staging());
+    const size_t row_bytes = row_bytes_of(p);
+    const size_t frame_bytes = stride * (static_cast<size_t>(p.height) - 1) + row_bytes;
+    const size_t frame_pitch = align_up(stride * static_cast<size_t>(p.height), 256);
+    size_t stream_slot = 0;
+    for (size_t i = 0; i < count; ++i)
+        stream_slot = frames[i].stream_capacity > stream_slot ? frames[i].stream_capacity : stream_slot;
+    stream_slot = align_up(stream_slot + 16, 256);
+    const size_t chunk = staging_chunk(count, frame_pitch + stream_slot);
+    for (int s = 0; s < 2; ++s)
+    {
+        JLS_CHECK(ensure(stage_pixels_[s], chunk * frame_pitch + 64));
+        JLS_CHECK(ensure(stage_streams_[s], chunk * stream_slot + 64));
+    }
+
+    const size_t chunks = (count + chunk - 1) / chunk;
+    std::vector<BatchFrame> staged(chunk);
+    const auto upload = [&](size_t j) -> int32_t {
+        const int s = static_cast<int>(j & 1U);
+        JLS_CUDA(cudaStreamWaitEvent(copy_in_, out_done_[s], 0));
+        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+        for (size_t k = 0; k < n; ++k)
+            JLS_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, frames[first + k].stream,
+                                     frames[first + k].stream_capacity, cudaMemcpyHostToDevice, copy_in_));
+        JLS_CUDA(cudaEventRecord(in_done_[s], copy_in_));
+        return 0;
+    };
+
+    int32_t first_error = 0;
+    JLS_CUDA(cudaEventRecord(out_done_[0], copy_out_));
+    JLS_CUDA(cudaEventRecord(out_done_[1], copy_out_));
+    JLS_CHECK(upload(0));
+    uint32_t launches = 0;
+    for (size_t j = 0; j < chunks; ++j)
+    {
+        const int s = static_cast<int>(j & 1U);
+        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+        for (size_t k = 0; k < n; ++k)
+            staged[k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
+                                   static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, frames[first + k].stream_capacity, 0, 0,
+                                   frames[first + k].scan_offset};
+        JLS_CUDA(cudaStreamWaitEvent(stream_, in_done_[s], 0));
+        const double t_before = g_trace.enabled ? g_trace.now() : 0.0;
+        const int32_t status =
+            decode_batch(p, staged.data(), n, stride, stream_, [&]() -> int32_t { return j + 1 < chunks ? upload(j + 1) : 0; });
+        if (g_trace.enabled)
+            std::fprintf(stderr, "decode_batch_host chunk %zu/%zu (%zu frames): decoded at %.3f ms, waited %.3f ms\n", j, chunks, n,
+                         g_trace.now(), g_trace.now() - t_before);
+        launches += last_launches_;
+        if (status != 0 && first_error == 0)
+            first_error = status;
+        for (size_t k = 0; k < n; ++k)
+        {
+            frames[first + k].status = staged[k].status;
+            frames[first + k].stream_size = staged[k].stream_size;
+            if (staged[k].status == 0)
+                JLS_CUDA(cudaMemcpyAsync(frames[first + k].pixels, staged[k].pixels, frame_bytes, cudaMemcpyDeviceToHost, copy_out_));
+        }
+        JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_));
+    }
+    const double t_drain = g_trace.enabled ? g_trace.now() : 0.0;
+    JLS_CHECK(wait_for(copy_out_));
+    if (g_trace.enabled)
+        std::fprintf(stderr, "decode_batch_host: drained at %.3f ms after %.3f ms\n", g_trace.now(), g_trace.now() - t_drain);
+    last_launches_ = launches;
     return first_error;
 }
 
@@ -661,7 +864,8 @@ int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32
     return 0;
 }
 
-int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream)
+int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream,
+                             const std::function<int32_t()>& while_coding)
 {
     JLS_CHECK(prepare());
     if (count == 0)
@@ -690,7 +894,12 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), static_cast<uint32_t>(count), max_remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
                            static_cast<uint8_t*>(marker_codes_.data), stream, events_, word_aligned));
-    JLS_CHECK(fetch_outcomes(count, stream));
+    JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
+    JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                             stream));
+    if (while_coding)
+        JLS_CHECK(while_coding());
+    JLS_CHECK(wait_for(stream));
     read_coder_time();
     last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
 

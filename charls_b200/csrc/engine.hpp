@@ -12,6 +12,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 struct CUstream_st;
@@ -58,9 +59,18 @@ public:
     int32_t decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed);
 
     // Device-resident batches (single-scan frames).  `header` = the bytes in front of the entropy-coded data.
+    // `while_coding` (optional) runs on the host after all work of the call has been issued and before the call waits
+    // for it: the host-resident path issues the next chunk's copies there, behind this chunk's kernels.
     int32_t encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
-                         size_t stride, CUstream_st* user_stream);
-    int32_t decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream);
+                         size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding = {});
+    int32_t decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream,
+                         const std::function<int32_t()>& while_coding = {});
+    // The same for frames and streams in HOST memory (pinned for full speed): the engine stages a chunk of frames at a
+    // time in device memory and overlaps the copies of one chunk with the kernels of its neighbours (three CUDA
+    // streams, double-buffered staging).  BatchFrame pointers are host pointers here.
+    int32_t encode_batch_host(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
+                              size_t stride);
+    int32_t decode_batch_host(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride);
     // Downloads the first `prefix_bytes` of every frame's stream (header parsing happens on the host).
     int32_t download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, std::vector<uint8_t>& prefixes,
                               CUstream_st* user_stream);
@@ -126,6 +136,14 @@ private:
     CUevent_st* events_[2]{};
     CUevent_st* sleep_event_{};
     std::vector<CachedGraph> graphs_;
+    // host-resident batches: staging slots and the two copy streams
+    int32_t prepare_staging();
+    static size_t staging_chunk(size_t count, size_t bytes_per_frame) noexcept;
+    Buffer stage_pixels_[2], stage_streams_[2];
+    CUstream_st* copy_in_{};
+    CUstream_st* copy_out_{};
+    CUevent_st* in_done_[2]{};
+    CUevent_st* out_done_[2]{};
     // CHARLS_B200_TRACE timeline of the single-image calls (engine.cu: Trace)
     void trace_gpu(int index) noexcept;
     void trace_host(int index) noexcept;

@@ -68,8 +68,12 @@ void charlsx_batch_destroy(charlsx_batch* batch) noexcept
     delete batch;
 }
 
-charls_jpegls_errc charlsx_batch_encode(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images,
-                                        size_t count, void* cuda_stream) noexcept
+} // extern "C"
+
+namespace {
+
+charls_jpegls_errc encode_frames(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images, size_t count,
+                                 void* cuda_stream, bool host_memory) noexcept
 {
     return guarded([&] {
         check_pointer(batch);
@@ -103,8 +107,10 @@ charls_jpegls_errc charlsx_batch_encode(charlsx_batch* batch, const charlsx_batc
             batch->frames[i] = BatchFrame{static_cast<uint8_t*>(images[i].pixels), static_cast<uint8_t*>(images[i].stream),
                                           images[i].stream_capacity, 0, 0, 0};
         }
-        const int32_t status = batch->engine.encode_batch(p, header, writer.bytes_written(), batch->frames.data(), count, stride,
-                                                          static_cast<CUstream_st*>(cuda_stream));
+        const int32_t status =
+            host_memory ? batch->engine.encode_batch_host(p, header, writer.bytes_written(), batch->frames.data(), count, stride)
+                        : batch->engine.encode_batch(p, header, writer.bytes_written(), batch->frames.data(), count, stride,
+                                                     static_cast<CUstream_st*>(cuda_stream));
         for (size_t i = 0; i < count; ++i)
         {
             images[i].stream_size = batch->frames[i].stream_size;
@@ -114,8 +120,28 @@ charls_jpegls_errc charlsx_batch_encode(charlsx_batch* batch, const charlsx_batc
     });
 }
 
-charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images,
+} // namespace
+
+extern "C" {
+
+charls_jpegls_errc charlsx_batch_encode(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images,
                                         size_t count, void* cuda_stream) noexcept
+{
+    return encode_frames(batch, params, images, count, cuda_stream, false);
+}
+
+charls_jpegls_errc charlsx_batch_encode_host(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images,
+                                             size_t count) noexcept
+{
+    return encode_frames(batch, params, images, count, nullptr, true);
+}
+
+} // extern "C"
+
+namespace {
+
+charls_jpegls_errc decode_frames(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images, size_t count,
+                                 void* cuda_stream, bool host_memory) noexcept
 {
     return guarded([&] {
         check_pointer(batch);
@@ -137,8 +163,10 @@ charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batc
             return;
 
         // headers are parsed on the host: one gather kernel + one copy brings the first bytes of every stream over
+        // (streams in host memory are read where they are)
         std::vector<uint8_t> prefixes;
-        check_status(batch->engine.download_prefixes(batch->frames.data(), count, header_prefix_bytes, prefixes, stream));
+        if (!host_memory)
+            check_status(batch->engine.download_prefixes(batch->frames.data(), count, header_prefix_bytes, prefixes, stream));
 
         bool have_params = false;
         CodecParams p{};
@@ -150,7 +178,7 @@ charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batc
             const size_t available = frame.stream_capacity < header_prefix_bytes ? frame.stream_capacity : header_prefix_bytes;
             const charls_jpegls_errc errc = guarded([&] {
                 StreamReader reader;
-                reader.source(prefixes.data() + i * header_prefix_bytes, available);
+                reader.source(host_memory ? frame.stream : prefixes.data() + i * header_prefix_bytes, available);
                 reader.read_header();
                 const charls_frame_info& info = reader.frame_info();
                 // every frame must match the batch description
@@ -188,7 +216,8 @@ charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batc
             std::vector<BatchFrame> work(active.size());
             for (size_t k = 0; k < active.size(); ++k)
                 work[k] = batch->frames[active[k]];
-            const int32_t status = batch->engine.decode_batch(p, work.data(), work.size(), stride, stream);
+            const int32_t status = host_memory ? batch->engine.decode_batch_host(p, work.data(), work.size(), stride)
+                                               : batch->engine.decode_batch(p, work.data(), work.size(), stride, stream);
             for (size_t k = 0; k < active.size(); ++k)
                 batch->frames[active[k]] = work[k];
             if (status != 0 && first_error == 0)
@@ -201,6 +230,22 @@ charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batc
         }
         check_status(first_error);
     });
+}
+
+} // namespace
+
+extern "C" {
+
+charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images,
+                                        size_t count, void* cuda_stream) noexcept
+{
+    return decode_frames(batch, params, images, count, cuda_stream, false);
+}
+
+charls_jpegls_errc charlsx_batch_decode_host(charlsx_batch* batch, const charlsx_batch_params* params, charlsx_batch_image* images,
+                                             size_t count) noexcept
+{
+    return decode_frames(batch, params, images, count, nullptr, true);
 }
 
 charls_jpegls_errc charlsx_batch_get_last_coder_kernel_ms(const charlsx_batch* batch, float* milliseconds) noexcept

@@ -369,6 +369,15 @@ CHARLS_B200_API charls_jpegls_errc charlsx_batch_encode(charlsx_batch* batch, co
                                                         charlsx_batch_image* images, size_t count, void* cuda_stream) CHARLS_B200_NOEXCEPT;
 CHARLS_B200_API charls_jpegls_errc charlsx_batch_decode(charlsx_batch* batch, const charlsx_batch_params* params,
                                                         charlsx_batch_image* images, size_t count, void* cuda_stream) CHARLS_B200_NOEXCEPT;
+/* The same for frames whose samples and streams live in HOST memory (`pixels` / `stream` are host pointers; page-locked
+   memory gives full PCIe speed): the library stages chunks of frames in device memory and overlaps the copies of one
+   chunk with the kernels of its neighbours, so one host thread keeps the PCIe link busy.  The reference's way to code many
+   images is one codec object and one call per image (include/charls/charls_jpegls_encoder.h:263-266,
+   charls_jpegls_decoder.h:168-172); these two calls replace such a loop. */
+CHARLS_B200_API charls_jpegls_errc charlsx_batch_encode_host(charlsx_batch* batch, const charlsx_batch_params* params,
+                                                             charlsx_batch_image* images, size_t count) CHARLS_B200_NOEXCEPT;
+CHARLS_B200_API charls_jpegls_errc charlsx_batch_decode_host(charlsx_batch* batch, const charlsx_batch_params* params,
+                                                             charlsx_batch_image* images, size_t count) CHARLS_B200_NOEXCEPT;
 /* Kernels launched by the last charlsx_batch_encode / _decode call on this object. */
 CHARLS_B200_API charls_jpegls_errc charlsx_batch_get_last_kernel_launches(const charlsx_batch* batch, uint32_t* launches) CHARLS_B200_NOEXCEPT;
 /* Device time (CUDA events on the launching stream, recorded directly around it) of the entropy-coding kernel of the

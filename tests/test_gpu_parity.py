@@ -366,3 +366,34 @@ def test_random_parameters_vs_oracle(product, oracle, seed):
         expected, _ = oracle.decode_image(got)
         px, _, _ = codec.decode(got, lib=product)
         assert np.array_equal(px, expected), case
+
+
+def test_host_batch_interface(product, oracle):
+    """charlsx_batch_encode_host / _decode_host: frames in host memory, staged through the device in chunks; the bytes
+    are those of the single-image ABI and a frame whose stream buffer is too small fails alone."""
+    from charls_b200.batch import BatchCodec
+
+    for (w, h, bits, cc, near, ilv, xf, n) in ((96, 40, 8, 1, 0, 0, 0, 7), (50, 21, 12, 1, 2, 0, 0, 3), (33, 17, 16, 3, 0, 2, 1, 5),
+                                               (512, 300, 8, 1, 0, 0, 0, 70)):
+        frames = [s_mixed(h, w, bits, cc, seed=50 + i, layout="interleaved") for i in range(n)]
+        bc = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, lib=product)
+        streams = [np.zeros(bc.stream_capacity * 2, np.uint8) for _ in range(n)]
+        sizes = bc.encode_host(frames, streams)
+        for i in (0, n // 2, n - 1):
+            single = encode(product, frames[i], bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf)
+            assert streams[i][: sizes[i]].tobytes() == single, (w, h, bits, i)
+        outputs = [np.zeros_like(f) for f in frames]
+        consumed = bc.decode_host(streams, sizes, outputs)
+        assert consumed == sizes
+        for i in range(n):
+            expected, _ = oracle.decode_image(streams[i][: sizes[i]].tobytes())
+            assert np.array_equal(outputs[i], expected), (w, h, bits, i)
+        # one stream buffer too small: that frame reports destination_too_small (3), the others are coded
+        small = [np.zeros(bc.stream_capacity * 2, np.uint8) for _ in range(n)]
+        small[1] = np.zeros(40, np.uint8)
+        with pytest.raises(CharlsError) as info:
+            bc.encode_host(frames, small)
+        assert info.value.errc == 3
+        assert small[0][: sizes[0]].tobytes() == streams[0][: sizes[0]].tobytes()
+        assert small[n - 1][: sizes[n - 1]].tobytes() == streams[n - 1][: sizes[n - 1]].tobytes()
+        bc.close()
