@@ -48,9 +48,13 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step (128 x 8 GPUs = BASELINE configs[4])")
     ap.add_argument("--e2e-frames", type=int, default=32)
     ap.add_argument("--e2e-threads", type=int, default=16)
+    ap.add_argument("--e2e-passes", type=int, default=4,
+                    help="every pinned frame buffer makes this many round trips per e2e step (32 x 4 = 128 frames per step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-phases", action="store_true", help="e2e: encode all frames, then decode all (default: per frame)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--also", default="auto", choices=["auto", "none"] + sorted(WORKLOADS),
+                    help="second workload reported under \"also\" (auto: cfg4 = 16-bit RGB beside cfg2, the metric names both)")
     ap.add_argument("--content", default="smooth", choices=["smooth", "noise", "flat"],
                     help="smooth = S_smooth (the metric's input); noise (uniform, incompressible) and flat (all zero, pure run "
                          "mode) bracket it (SURVEY.md 8d)")
@@ -262,8 +266,9 @@ def workload_name(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
-def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads, pipelined=True):
-    """Through the C ABI with pinned host buffers: every frame encoded, then every stream decoded. Returns (s, sizes)."""
+def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads, pipelined=True, passes=1):
+    """Through the C ABI with pinned host buffers: every frame buffer is encoded and its stream decoded `passes` times (a
+    worker owns buffers t, t + threads, ... so no buffer is ever in two calls at once). Returns (s, sizes)."""
     from charls_b200.capi import FrameInfo
 
     w, h, bits, cc, near, ilv, xf = WORKLOADS[workload]
@@ -297,16 +302,71 @@ def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads, 
         enc(i)
         dec(i)
 
+    def worker(t):
+        # every worker encodes a frame and decodes it right away: both PCIe directions carry raw and compressed bytes
+        # all the time instead of raw going up in one phase and coming down in the next
+        for _ in range(passes):
+            for i in range(t, n, threads):
+                both(i)
+
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as pool:
         if pipelined:
-            # every worker encodes a frame and decodes it right away: both PCIe directions carry raw and compressed
-            # bytes all the time instead of raw going up in one phase and coming down in the next
-            list(pool.map(both, range(n)))
+            list(pool.map(worker, range(threads)))
         else:
-            list(pool.map(enc, range(n)))
-            list(pool.map(dec, range(n)))
+            for _ in range(passes):
+                list(pool.map(enc, range(n)))
+                list(pool.map(dec, range(n)))
     return time.perf_counter() - t0, sizes
+
+
+def secondary_workload(torch, dist, lib, device, rank, world, workload, F, steps, peak):
+    """The metric names two inputs (8-bit mono and 16-bit RGB): the other one, measured like `value` (device-resident frames,
+    CUDA events on the coder stream, max over ranks) with fewer frames and steps, reported under "also"."""
+    from charls_b200.batch import BatchCodec
+
+    w, h, bits, cc, near, ilv, xf = WORKLOADS[workload]
+    frames = make_frames(torch, device, F, workload, first_seed=1234 + rank * F)
+    codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=1, lib=lib)
+    streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
+    decoded = torch.empty_like(frames)
+    raw_bytes = frames[0].numel() * frames.element_size()
+    for _ in range(3):
+        sizes = codec.encode(frames, streams)
+        codec.decode(streams, sizes, decoded)
+    torch.cuda.synchronize()
+    assert near != 0 or torch.equal(decoded, frames), "round trip mismatch"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    enc_ms, dec_ms = [], []
+    start.record()
+    for _ in range(steps):
+        sizes = codec.encode(frames, streams)
+        enc_ms.append(codec.last_coder_kernel_ms())
+        codec.decode(streams, sizes, decoded)
+        dec_ms.append(codec.last_coder_kernel_ms())
+    stop.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([start.elapsed_time(stop) / steps, float(np.mean(enc_ms)), float(np.mean(dec_ms))], device=device, dtype=torch.float64)
+    comp = torch.tensor([float(sum(sizes))], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(comp, op=dist.ReduceOp.SUM)
+    del frames, streams, decoded
+    torch.cuda.empty_cache()
+    ms, t_enc, t_dec = (float(v) for v in t.tolist())
+    comp_per_frame = float(comp.item()) / (world * F)
+    pixels = world * F * w * h
+    algorithmic = F * (raw_bytes + comp_per_frame)
+    return {
+        "workload": f"{workload}: {w}x{h} {bits}-bit x{cc} NEAR={near} ILV={ilv} HP{xf} restart-interval=1, {F} frames per GPU per step",
+        "value": pixels / (ms * 1e-3) / 1e6, "unit": "MPixels/s", "ms_per_step": ms, "steps": steps, "dtype": "u8" if bits <= 8 else "u16",
+        "encode_mpix_s": pixels / (t_enc * 1e-3) / 1e6, "decode_mpix_s": pixels / (t_dec * 1e-3) / 1e6,
+        "ratio": raw_bytes / comp_per_frame,
+        "roofline_frac": {"encode": algorithmic / (t_enc * 1e-3) / 1e9 / peak, "decode": algorithmic / (t_dec * 1e-3) / 1e9 / peak},
+    }
 
 
 def run_gpu_arm(args):
@@ -410,12 +470,13 @@ def run_gpu_arm(args):
         threads = max(1, min(args.e2e_threads, effective_cpus()))
         for _ in range(3):
             e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads, not args.e2e_phases)
+        passes = max(1, args.e2e_passes)
         if world > 1:
             dist.barrier()
         t_e2e, e2e_sizes = 0.0, None
         reps = max(3, args.steps)
         for _ in range(reps):
-            dt, e2e_sizes = e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads, not args.e2e_phases)
+            dt, e2e_sizes = e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads, not args.e2e_phases, passes)
             t_e2e += dt
         if near == 0:
             assert torch.equal(out_host, frames_host), "e2e round trip mismatch"
@@ -424,9 +485,9 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         comp = sum(e2e_sizes)
         e2e = {
-            "value": world * n * w * h / float(t.item()) / 1e6, "unit": "MPixels/s",
-            "h2d_bytes_per_step": world * (n * raw_bytes + comp), "d2h_bytes_per_step": world * (comp + n * raw_bytes),
-            "frames_per_step": world * n, "host_threads": threads,
+            "value": world * passes * n * w * h / float(t.item()) / 1e6, "unit": "MPixels/s",
+            "h2d_bytes_per_step": world * passes * (n * raw_bytes + comp), "d2h_bytes_per_step": world * passes * (comp + n * raw_bytes),
+            "frames_per_step": world * passes * n, "pinned_frame_buffers": world * n, "host_threads": threads,
             "order": "all frames encoded, then all decoded" if args.e2e_phases else "each frame encoded and decoded by one worker",
             "api": "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
         }
@@ -455,17 +516,26 @@ def run_gpu_arm(args):
             "api": "charlsx_batch_encode_host, then charlsx_batch_decode_host (extension), same pinned host buffers",
         }
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_kind = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_kind = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- the metric's other input (16-bit RGB when the headline workload is the 8-bit one, and the other way round)
+    also = None
+    if args.also != "none" and args.content == "smooth":
+        other = ("cfg4" if args.workload != "cfg4" else "cfg2") if args.also == "auto" else args.also
+        del frames, streams, decoded
+        torch.cuda.empty_cache()
+        also = {other: secondary_workload(torch, dist, lib, device, rank, world, other, max(1, args.frames // 2), max(3, args.steps // 4), peak)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the entropy-coding kernels (algorithmic bytes = raw + compressed)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_kind = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_kind = 6650.0, "fallback (B200_PROFILING.md)"
     algorithmic = F * (raw_bytes + comp_per_frame)
     t_enc, t_dec = float(kernel_ms[0].item()), float(kernel_ms[1].item())
     traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -504,7 +574,7 @@ def run_gpu_arm(args):
                    "cache": f"inputs larger than L2: {F * raw_bytes / 1e6:.0f} MB raw + {F * comp_per_frame / 1e6:.0f} MB streams per GPU vs 126 MB L2",
                    "sharding": "frames split across ranks, no data-path collective; NCCL all_gather of stream sizes only"},
         "encode_mpix_s": world * F * w * h / (t_enc * 1e-3) / 1e6, "decode_mpix_s": world * F * w * h / (t_dec * 1e-3) / 1e6,
-        "roofline": dominant, "roofline_all": roofs, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+        "roofline": dominant, "roofline_all": roofs, "cpu_baseline": cpu_baseline, "e2e": e2e, "also": also, "clocks": clocks,
         "gpu_launches": int(launches_after.value - launches_before.value),
     }
     print(json.dumps(out))

@@ -227,6 +227,29 @@ int32_t Engine::wait_for(CUstream_st* stream)
     return 0;
 }
 
+// The address under which the device can write `pointer` directly, or null for ordinary pageable host memory.
+// Opt-in (CHARLS_B200_DIRECT_OUTPUT=1): it saves the encoder's second wait, but 128-byte stores over PCIe are slower than
+// the copy engine's transfers -- with 16 callers on one B200 the round-trip rate fell from 24.9 to 22.0 GPix/s
+// (profiles/r1_notes.md), so the staged copy stays the default.
+uint8_t* Engine::device_view_of(void* pointer) noexcept
+{
+    const char* value = std::getenv("CHARLS_B200_DIRECT_OUTPUT");
+    const bool enabled = value && value[0] == '1';
+    if (!enabled || !pointer)
+        return nullptr;
+    cudaPointerAttributes attributes{};
+    if (cudaPointerGetAttributes(&attributes, pointer) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (attributes.type == cudaMemoryTypeUnregistered || !attributes.devicePointer)
+        return nullptr;
+    if (attributes.type == cudaMemoryTypeDevice && attributes.device != device_)
+        return nullptr; // another GPU's memory: take the staged copy
+    return static_cast<uint8_t*>(attributes.devicePointer);
+}
+
 void Engine::trace_gpu(int index) noexcept
 {
     if (!g_trace.enabled)
@@ -469,13 +492,19 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
         return 7; // parameter_value_not_supported: one restart interval must stay below 4 GiB of entropy-coded data
     const size_t worst_total = static_cast<size_t>(p.interval_count) * (slot_bytes + 2);
     const size_t device_capacity = capacity < worst_total ? capacity : worst_total;
-    JLS_CHECK(ensure(stream_buffer_, device_capacity + 64));
+    // Opt-in: a destination the device can address (page-locked or registered host memory) is written by the gather
+    // kernel itself -- no staging buffer, no second copy whose size the host has to wait for first (see device_view_of).
+    uint8_t* direct = device_view_of(destination);
+    if (direct && device_capacity > 1 && !device_view_of(destination + device_capacity - 1))
+        direct = nullptr; // only the beginning of the buffer is registered
+    if (!direct)
+        JLS_CHECK(ensure(stream_buffer_, device_capacity + 64));
 
     std::vector<ScanJob> jobs(1);
     jobs[0] = ScanJob{};
     jobs[0].pixels_in = static_cast<const uint8_t*>(pixels_.data);
     jobs[0].stride = pitch;
-    jobs[0].stream_out = static_cast<uint8_t*>(stream_buffer_.data);
+    jobs[0].stream_out = direct ? direct : static_cast<uint8_t*>(stream_buffer_.data);
     jobs[0].stream_out_capacity = device_capacity;
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_, false));
     JLS_CHECK(ensure(host_outcomes_, outcome_words * sizeof(uint64_t), true));
@@ -503,7 +532,7 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     const uint64_t total = outcome[1];
     if (total > capacity)
         return err_destination_too_small;
-    if (total != 0)
+    if (total != 0 && !direct)
     {
         JLS_CUDA(cudaMemcpyAsync(destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
         trace_gpu(3);
@@ -568,22 +597,28 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
         return 0;
     }));
     trace_gpu(2);
+    // The samples follow the kernels without a host round trip in between: the caller's buffer is specified only for a
+    // successful decode (the reference leaves the lines it got to before the error), so nothing is lost when the
+    // outcome turns out to be an error.
+    if (stride == pitch)
+        JLS_CUDA(cudaMemcpyAsync(destination, pixels_.data, pitch * (static_cast<size_t>(p.height) - 1) + row_bytes,
+                                 cudaMemcpyDeviceToHost, stream_));
+    else
+        JLS_CUDA(cudaMemcpy2DAsync(destination, stride, pixels_.data, pitch, row_bytes, static_cast<size_t>(p.height),
+                                   cudaMemcpyDeviceToHost, stream_));
+    trace_gpu(3);
     trace_host(1);
     JLS_CHECK(wait_for(stream_));
     trace_host(2);
     last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
     last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
+    trace_host(3);
+    trace_commit(1);
 
     const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
     if (outcome[0] != ~0ULL)
         return static_cast<int32_t>(outcome[0] & 0xFF);
     consumed = static_cast<size_t>(outcome[1]);
-    JLS_CUDA(cudaMemcpy2DAsync(destination, stride, pixels_.data, pitch, row_bytes, static_cast<size_t>(p.height),
-                               cudaMemcpyDeviceToHost, stream_));
-    trace_gpu(3);
-    JLS_CHECK(wait_for(stream_));
-    trace_host(3);
-    trace_commit(1);
     return 0;
 }
 

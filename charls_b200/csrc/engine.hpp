@@ -146,6 +146,7 @@ private:
     CUevent_st* out_done_[2]{};
     // CHARLS_B200_TRACE timeline of the single-image calls (engine.cu: Trace)
     void trace_gpu(int index) noexcept;
+    uint8_t* device_view_of(void* pointer) noexcept;
     void trace_host(int index) noexcept;
     void trace_commit(int kind) noexcept;
     CUevent_st* trace_events_[4]{};

@@ -397,3 +397,46 @@ def test_host_batch_interface(product, oracle):
         assert small[0][: sizes[0]].tobytes() == streams[0][: sizes[0]].tobytes()
         assert small[n - 1][: sizes[n - 1]].tobytes() == streams[n - 1][: sizes[n - 1]].tobytes()
         bc.close()
+
+
+@pytest.mark.parametrize("direct", ["1", "0"])
+def test_page_locked_destination(product, oracle, direct, monkeypatch):
+    """Page-locked host buffers through the single-image ABI.  With CHARLS_B200_DIRECT_OUTPUT=1 the gather kernel writes
+    the caller's destination itself (any alignment, next to untouched bytes); the bytes equal those of the staged copy
+    into pageable memory, and a destination that is too small reports destination_too_small without a write beyond
+    its end."""
+    import torch
+
+    monkeypatch.setenv("CHARLS_B200_DIRECT_OUTPUT", direct)
+
+    from charls_b200.codec import JpegLSEncoder
+
+    cases = ((8, 1, 0, 0, 0, 1), (12, 1, 2, 0, 0, 1), (16, 3, 0, 2, 1, 1), (8, 3, 0, 0, 0, 1), (8, 1, 0, 0, 0, 0), (8, 3, 0, 1, 0, 3))
+    for case, (bits, cc, near, ilv, xf, ri) in enumerate(cases):
+        layout = "planar" if ilv == 0 else "interleaved"
+        image = s_mixed(61, 333, bits, cc, seed=90 + case, layout=layout) if cc > 1 else s_mixed(61, 333, bits, seed=90 + case)
+        want = encode(product, image, bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=ri)
+        h, w, c = codec._shape_info(image, ilv)
+        for lead in (0, 1, 3, 6):
+            pinned = torch.full((lead + len(want) + 64,), 0xA5, dtype=torch.uint8).pin_memory()
+            view = pinned.numpy()[lead : lead + len(want) + 32]
+            with JpegLSEncoder(product) as enc:
+                enc.frame_info(w, h, bits, c).near_lossless(near).interleave_mode(ilv).color_transformation(xf).restart_interval(ri)
+                enc.destination(view)
+                n = enc.encode(image)
+            assert view[:n].tobytes() == want, (case, lead)
+            assert (pinned.numpy()[:lead] == 0xA5).all() and (pinned.numpy()[lead + n + 32 :] == 0xA5).all(), (case, lead)
+            expected, _ = oracle.decode_image(want)
+            out = torch.zeros(image.nbytes, dtype=torch.uint8).pin_memory()
+            with codec.JpegLSDecoder(product) as dec:
+                dec.source(view[:n]).read_header()
+                dec.decode(out.numpy())
+            assert out.numpy().tobytes() == np.ascontiguousarray(expected).tobytes(), (case, lead)
+        short = torch.full((len(want) - 9 + 64,), 0x5A, dtype=torch.uint8).pin_memory()
+        with JpegLSEncoder(product) as enc:
+            enc.frame_info(w, h, bits, c).near_lossless(near).interleave_mode(ilv).color_transformation(xf).restart_interval(ri)
+            enc.destination(short.numpy()[: len(want) - 9])
+            with pytest.raises(CharlsError) as info:
+                enc.encode(image)
+        assert info.value.errc == 3
+        assert (short.numpy()[len(want) - 9 :] == 0x5A).all(), case
