@@ -118,6 +118,7 @@ JLS_HD uint32_t has_ff_byte(uint32_t w)
 JLS_HD int32_t iabs(int32_t v) { return v < 0 ? -v : v; }
 JLS_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
 JLS_HD int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+JLS_HD uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // reference src/jpegls_algorithm.hpp:91-116
 JLS_HD int32_t bit_wise_sign(int32_t v) { return v >> 31; }

@@ -32,14 +32,46 @@ struct HotParams
 {
     int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init;
     uint32_t dq_magic;
+    uint32_t sign_scale; // 2^(32 - bits)
     // Optional table |Q(-Ra)| for Ra in [0, context_lut_last]; larger Ra use the last entry (they are >= T3).  The tile
     // kernels keep it in shared memory: one LDS replaces three compares, a select and the adds on the busy ALU pipe.
     const uint8_t* context_lut;
     int32_t context_lut_last;
     uint32_t context_lut_shared; // device: shared-window address of context_lut (see keep_hot_params_in_registers)
+    // Optional table ceil(2^31 / N) for N in [0, RESET] (entry 0 unused): with it the Golomb parameter is two multiplies on
+    // the FMA pipe and one find-leading-one instead of two find-leading-one, a clamp, a shift, a compare and a select
+    // (golomb_parameter_reciprocal).
+    const uint32_t* reciprocal_lut;
+    uint32_t reciprocal_lut_shared;
 };
 
 constexpr int32_t context_lut_capacity = 1024; // the table covers T3 <= 1023 (defaults: 21 / 85 / 276 for 8 / 12 / 16 bit)
+// The table form of the Golomb parameter is exact for N <= 64 and A < 2^24 (checked exhaustively, tests/test_hostemu.py);
+// N runs up to RESET (default 64 for every bit depth), larger RESET values take the kernels without tables.
+constexpr int32_t reciprocal_lut_capacity = 65;
+
+JLS_HD uint32_t reciprocal_lut_entry(int32_t n)
+{
+    if (n <= 1)
+        return 0x7FFFFFFFU; // n = 1: floor((2a - 1) * (2^31 - 1) / 2^32) = a - 1 exactly, and the factor stays positive
+    return static_cast<uint32_t>(((1ULL << 31) + static_cast<uint64_t>(n) - 1U) / static_cast<uint64_t>(n));
+}
+
+// min k with (n << k) >= a, from reciprocal = ceil(2^31 / n):  k = bit length of floor((a - 1) / n), and
+// t = floor((2a - 1) * reciprocal / 2^32) has that bit length for n <= 64, a < 2^24 (the quotient is overestimated by
+// less than what it takes to reach the next power of two).  a = 0 gives t = -1, whose most significant non-sign bit
+// does not exist: k = 0 like the reference.  Any a gives 0 <= k <= 31.
+JLS_HD int32_t golomb_parameter_reciprocal(int32_t a, uint32_t reciprocal)
+{
+#if defined(__CUDA_ARCH__)
+    int32_t position;
+    asm("bfind.s32 %0, %1;" : "=r"(position) : "r"(__mulhi(2 * a - 1, static_cast<int32_t>(reciprocal))));
+    return position + 1; // bfind yields -1 for 0 and for -1
+#else
+    const int64_t t = (static_cast<int64_t>(static_cast<int32_t>(2U * static_cast<uint32_t>(a) - 1U)) * static_cast<int64_t>(reciprocal)) >> 32;
+    return t < 0 ? 32 - clz32(static_cast<uint32_t>(~t)) : 32 - clz32(static_cast<uint32_t>(t));
+#endif
+}
 
 JLS_HD HotParams make_hot_params(const CodecParams& p)
 {
@@ -59,9 +91,12 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.range_dq = p.range_dq;
     h.a_init = p.a_init;
     h.dq_magic = p.dq_magic;
+    h.sign_scale = 1U << (32 - p.bits_per_sample);
     h.context_lut = nullptr;
     h.context_lut_last = 0;
     h.context_lut_shared = 0;
+    h.reciprocal_lut = nullptr;
+    h.reciprocal_lut_shared = 0;
     return h;
 }
 
@@ -83,6 +118,9 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
         scratch[6] = h.maxval;
         scratch[7] = h.bits;
         scratch[8] = static_cast<int32_t>(h.context_lut_shared);
+        scratch[9] = static_cast<int32_t>(h.reciprocal_lut_shared);
+        scratch[10] = static_cast<int32_t>(h.sign_scale);
+        scratch[11] = h.context_lut_last;
     }
     __syncwarp();
     h.t1 = scratch[0];
@@ -94,8 +132,11 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
     h.maxval = scratch[6];
     h.bits = scratch[7];
     h.context_lut_shared = static_cast<uint32_t>(scratch[8]); // same story for an address that derives from the CTA id
+    h.reciprocal_lut_shared = static_cast<uint32_t>(scratch[9]);
+    h.sign_scale = static_cast<uint32_t>(scratch[10]);
+    h.context_lut_last = scratch[11];
 }
-constexpr int hot_scratch_words = 9;
+constexpr int hot_scratch_words = 12;
 #endif
 
 template<bool LOSSLESS>
@@ -103,8 +144,9 @@ JLS_HD int32_t fast_error_value(const HotParams& h, int32_t e)
 {
     if (LOSSLESS)
     {
-        const int32_t shift = 32 - h.bits;
-        return static_cast<int32_t>(static_cast<uint32_t>(e) << shift) >> shift;
+        // modulo RANGE = sign extension from bit `bits` (reference src/lossless_traits.hpp:61-65); the left shift is a
+        // multiplication so that it goes to the FMA pipe, the integer ALU pipe is the busy one
+        return static_cast<int32_t>(static_cast<uint32_t>(e) * h.sign_scale) >> (32 - h.bits);
     }
     int32_t q = static_cast<int32_t>(mulhi32(static_cast<uint32_t>(iabs(e) + h.near), h.dq_magic));
     q = e > 0 ? q : -q;
@@ -133,15 +175,19 @@ JLS_HD int32_t fast_reconstruct(const HotParams& h, int32_t predicted, int32_t e
     return fast_clamp(h, v);
 }
 
-// T.87 A.12 / A.13 (reference src/regular_mode_context.hpp:45-94); branch-light.  Returns non-zero where the reference's
-// sanity check (:52-54, a >= 2^24 or |b| >= 2^24 before the halving and clamping) fires; only the decoder looks at it.
-// With NEAR = 0, |b| stays below RESET + 65535 and is not tested.
+// T.87 A.12 / A.13 (reference src/regular_mode_context.hpp:45-94); branch-light.
+// The reference's sanity check (:52-54: A >= 2^24 or |B| >= 2^24 before the halving and clamping) is kept as a high-water
+// mark that only the decoder looks at: the return value is the maximum of everything that must stay below
+// sanity_limit = 2^24 (the decoder adds k << 20 and |e| << 8, whose bounds land on the same limit).  Three-input
+// maxima replace a shift per quantity and the ORs.  With NEAR = 0, |B| stays below RESET + 65535 and is not looked at.
+constexpr uint32_t sanity_limit = 1U << 24;
+
 template<bool LOSSLESS>
 JLS_HD uint32_t fast_update_context(const HotParams& h, RegularContext& c, int32_t e)
 {
     c.a += iabs(e);
     c.b += LOSSLESS ? e : e * h.dq;
-    const uint32_t insane = static_cast<uint32_t>(LOSSLESS ? c.a : (c.a | iabs(c.b))) >> 24;
+    const uint32_t water = LOSSLESS ? static_cast<uint32_t>(c.a) : umax(static_cast<uint32_t>(c.a), static_cast<uint32_t>(iabs(c.b)));
     if (JLS_UNLIKELY(c.n == h.reset))
     {
         c.a >>= 1;
@@ -158,7 +204,7 @@ JLS_HD uint32_t fast_update_context(const HotParams& h, RegularContext& c, int32
     const int32_t c_high = imin(c.c + 1, 127);
     c.b = low ? b_low : (high ? b_high : c.b);
     c.c = low ? c_low : (high ? c_high : c.c);
-    return insane;
+    return water;
 }
 
 // Fills entry `index` of the context table (callers loop / stride over [0, last]).
@@ -594,6 +640,7 @@ struct FastLineState
 #endif
     RegularContext cached;
     int32_t cached_index;
+    uint32_t cached_reciprocal; // USE_LUT: reciprocal_lut[cached.n], reloaded whenever cached.n changes
     RunContext run_context; // scalar lines only ever use RItype 1, multi-component pixels only RItype 0
     int32_t run_index;
     int32_t ra[NC];
@@ -642,6 +689,7 @@ struct FastLineState
             store_context(q, initial);
         cached = initial;
         cached_index = 4;
+        cached_reciprocal = reciprocal_lut_entry(1);
         run_context.a = h.a_init;
         run_context.n = 1;
         run_context.nn = 0;
@@ -657,14 +705,42 @@ struct FastLineState
             ra[c] = 0;
     }
 
-    JLS_HD void select_context(int32_t index)
+    JLS_HD void select_context(const HotParams& h, int32_t index)
     {
-        if (index != cached_index)
+        // a branch, not predication: seven instructions that a warp skips for as long as its lines stay in their contexts
+        if (JLS_UNLIKELY(index != cached_index))
         {
             store_context(cached_index, cached);
             cached = load_context(index);
             cached_index = index;
+            if (USE_LUT)
+                load_reciprocal(h);
         }
+    }
+
+    // after cached.n changed
+    JLS_HD void load_reciprocal(const HotParams& h)
+    {
+#if defined(__CUDA_ARCH__)
+        asm("ld.shared.u32 %0, [%1];" : "=r"(cached_reciprocal) : "r"(h.reciprocal_lut_shared + 4U * static_cast<uint32_t>(cached.n)));
+#else
+        cached_reciprocal = h.reciprocal_lut[cached.n];
+#endif
+    }
+
+    JLS_HD int32_t golomb_k() const
+    {
+        return USE_LUT ? golomb_parameter_reciprocal(cached.a, cached_reciprocal) : golomb_parameter(cached.a, cached.n);
+    }
+
+    // context update of the cached context; returns the high-water mark of fast_update_context
+    template<bool LOSSLESS>
+    JLS_HD uint32_t update(const HotParams& h, int32_t e)
+    {
+        const uint32_t water = fast_update_context<LOSSLESS>(h, cached, e);
+        if (USE_LUT)
+            load_reciprocal(h);
+        return water;
     }
 
     // |Q(-Ra)|: di = -Ra <= -T3 -> 4, <= -T2 -> 3, <= -T1 -> 2, < -NEAR -> 1, else 0 (jpegls_algorithm.hpp:173-194)
@@ -727,9 +803,9 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
     JLS_HD int32_t regular(const HotParams& h, int32_t x, int32_t ra_value)
     {
         const int32_t q = FastLineState<NC, USE_LUT>::context_index(h, ra_value);
-        this->select_context(q);
+        this->select_context(h, q);
         RegularContext& c = this->cached;
-        const int32_t k = golomb_parameter(c.a, c.n);
+        const int32_t k = this->golomb_k();
         const bool negative = NC == 1 || q != 0; // a scalar line reaches regular mode only with q != 0
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
         const int32_t e = fast_error_value<LOSSLESS>(h, negative ? pv - x : x - pv);
@@ -737,7 +813,7 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
         // (src/scan_encoder_core.hpp:48-53, src/regular_mode_context.hpp:36-42) costs one conditional bit flip here
         const bool flip = (LOSSLESS ? k : (k | h.near)) == 0 && 2 * c.b + c.n < 1;
         bw.template put_golomb<DEFERRED>(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
-        fast_update_context<LOSSLESS>(h, c, e);
+        this->template update<LOSSLESS>(h, e);
         return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
     }
 
@@ -822,17 +898,17 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
     // register and one test on the regular-mode path
     int32_t pending;
-    uint32_t insane_seen; // sticky: one of the reference's sanity checks fired in regular mode
+    uint32_t high_water; // >= sanity_limit: one of the reference's sanity checks fired in regular mode (fast_update_context)
 
     JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, const uint8_t* begin_, const uint8_t* end_)
     {
         this->begin_interval(h, ctx, stride);
         br.init(begin_, end_);
         pending = 0;
-        insane_seen = 0;
+        high_water = 0;
     }
 
-    JLS_HD bool bad() const { return (br.bad | insane_seen) != 0; }
+    JLS_HD bool bad() const { return br.bad != 0 || high_water >= sanity_limit; }
 
     // called by the pixel loop every few pixels, by all lanes at the same time (see FastReader)
     JLS_HD void top_up() { br.top_up(); }
@@ -847,20 +923,20 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
     JLS_HD int32_t regular(const HotParams& h, int32_t ra_value)
     {
         const int32_t q = FastLineState<NC, USE_LUT>::context_index(h, ra_value);
-        this->select_context(q);
+        this->select_context(h, q);
         RegularContext& c = this->cached;
         const bool negative = NC == 1 || q != 0;
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
-        const int32_t k = golomb_parameter(c.a, c.n);
-        // The reference rejects k >= 16 (src/regular_mode_context.hpp:107-108).  No branch and no clamp: the flag is
-        // sticky, a < 2^24 bounds k by 24 and the reader takes any k <= 31.
-        uint32_t insane = static_cast<uint32_t>(k) >> 4;
+        const int32_t k = this->golomb_k();
         const bool flip = k == 0 && (LOSSLESS || h.near == 0) && 2 * c.b + c.n < 1; // see the encoder
         const int32_t e = unmap_error_value(br.get_golomb_steady(h, k, h.escape) ^ (flip ? 1 : 0));
-        // the reference's sanity checks: |e| > 65535 (src/scan_decoder_core.hpp:57-58) and the context's (:52-54)
-        insane |= static_cast<uint32_t>(iabs(e)) >> 16;
-        insane |= fast_update_context<LOSSLESS>(h, c, e);
-        insane_seen |= insane; // a flag of its own: br.bad is written on the rare paths and would be copied around them
+        // The reference's sanity checks -- k >= 16 (src/regular_mode_context.hpp:107-108), |e| > 65535
+        // (src/scan_decoder_core.hpp:57-58) and the context's (:52-54) -- without branches or clamps: each quantity is
+        // scaled so that its bound is sanity_limit and goes into a running maximum.  k <= 31 and |e| < 2^22 on every
+        // path (24 or `escape` zeros at most, shifted by k <= 15, or k >= 16 which trips the limit by itself), so the
+        // products cannot wrap.
+        const uint32_t marks = umax(static_cast<uint32_t>(k) << 20, static_cast<uint32_t>(iabs(e)) << 8);
+        high_water = umax(umax(high_water, marks), this->template update<LOSSLESS>(h, e));
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }
 
@@ -918,12 +994,13 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
         br.top_up();
     }
 
-    // Decodes one pixel into this->ra. `remaining` = pixels left in the line including this one.
-    JLS_HD void pixel(const HotParams& h, int32_t remaining)
+    // Decodes one pixel into this->ra. remaining_a + remaining_b = pixels left in the line including this one (the sum
+    // is needed on the run-mode path only and is formed there).
+    JLS_HD void pixel(const HotParams& h, int32_t remaining_a, int32_t remaining_b)
     {
         if (JLS_UNLIKELY((pending != 0) | this->in_run_mode(h)))
         {
-            run_mode_pixel(h, remaining);
+            run_mode_pixel(h, remaining_a + remaining_b);
             return;
         }
 #pragma unroll

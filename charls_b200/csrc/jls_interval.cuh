@@ -83,15 +83,17 @@ JLS_HD void fast_store_pixel(const CodecParams& p, S* line, int32_t x, const int
 }
 
 // LINE_ILV: the interval holds one line of each of p.components components (line interleave); NC must be 1 then.
-// USE_LUT: context_lut holds context_lut_entry(p, 0 .. min(T3, capacity - 1)).
+// USE_LUT: context_lut holds context_lut_entry(p, 0 .. min(T3, capacity - 1)), reciprocal_lut holds
+// reciprocal_lut_entry(0 .. RESET) (RESET < reciprocal_lut_capacity).
 template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, bool USE_LUT = false>
 JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
                                            RegularContext* contexts, int32_t context_stride, size_t slot_bytes,
-                                           const uint8_t* context_lut = nullptr)
+                                           const uint8_t* context_lut = nullptr, const uint32_t* reciprocal_lut = nullptr)
 {
     HotParams h = make_hot_params(p);
     h.context_lut = context_lut;
     h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
+    h.reciprocal_lut = reciprocal_lut;
     FastLineEncoder<NC, LOSSLESS, USE_LUT, !(LOSSLESS && sizeof(S) == 2)> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(interval) * slot_bytes;
     assume_global(slot);
@@ -162,7 +164,7 @@ JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool 
 template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, bool USE_LUT = false>
 JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
                                            RegularContext* contexts, int32_t context_stride,
-                                           const uint8_t* context_lut = nullptr)
+                                           const uint8_t* context_lut = nullptr, const uint32_t* reciprocal_lut = nullptr)
 {
     IntervalResult result = {err_none, 0};
     // interval_offset holds 2 entries per interval: [2i] = first byte, [2i+1] = end (first 0xFF of the closing marker)
@@ -179,6 +181,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
     HotParams h = make_hot_params(p);
     h.context_lut = context_lut;
     h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
+    h.reciprocal_lut = reciprocal_lut;
     FastLineDecoder<NC, LOSSLESS, USE_LUT> dec;
     dec.begin(h, contexts, context_stride, job.stream_in + begin, job.stream_in + end);
     S* line = reinterpret_cast<S*>(job.pixels_out + static_cast<size_t>(interval) * job.stride);
@@ -198,7 +201,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
                 {
                     if (x % dec.pixels_per_top_up == 0)
                         dec.top_up();
-                    dec.pixel(h, width - x);
+                    dec.pixel(h, width, -x);
                     line[x * nc + c] = static_cast<S>(dec.ra[0]);
                 }
             }
@@ -221,7 +224,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
         {
             if (x % dec.pixels_per_top_up == 0)
                 dec.top_up();
-            dec.pixel(h, width - x);
+            dec.pixel(h, width, -x);
             fast_store_pixel<NC, S>(p, line, x, dec.ra);
         }
     }

@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(fast_block_threads)
     const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
     for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
         context_lut[i] = context_lut_entry(p, i);
+    __shared__ uint32_t reciprocal_lut[reciprocal_lut_capacity]; // the host only picks this kernel when RESET <= 64
+    for (int32_t i = threadIdx.x; i < reciprocal_lut_capacity; i += fast_block_threads)
+        reciprocal_lut[i] = reciprocal_lut_entry(i);
     __syncthreads();
 
     const ScanJob& job = jobs[blockIdx.y];
@@ -111,6 +114,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.context_lut = context_lut;
     h.context_lut_last = lut_last;
     h.context_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(context_lut));
+    h.reciprocal_lut = reciprocal_lut;
+    h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
     FastLineEncoder<NC, LOSSLESS, true, !(LOSSLESS && sizeof(S) == 2)> enc;
@@ -145,27 +150,33 @@ __global__ void __launch_bounds__(fast_block_threads)
         {
             const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
             // two loop registers: the sample pointer and a count-down that is loop condition and drain cadence at once
+            // (pixels_per_tile is a multiple of 4: groups end where n is one)
             int32_t n = min(pixels_per_tile, width - t * pixels_per_tile);
-            for (; n != 0; sample += NC, --n)
+            do
             {
-                if ((n & 3) == 0)
-                    enc.drain(); // every fourth pixel, for all lanes of the warp together
-                int32_t v[NC];
-#pragma unroll
-                for (int32_t c = 0; c < NC; ++c)
-                    v[c] = sample[c];
-                if (NC == 3 && transform != 0)
+                enc.drain(); // every fourth pixel, for all lanes of the warp together
+#pragma unroll 1
+                do
                 {
-                    color_forward(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
-                }
-                else if (mask_needed)
-                {
+                    int32_t v[NC];
 #pragma unroll
                     for (int32_t c = 0; c < NC; ++c)
-                        v[c] &= h.maxval;
-                }
-                enc.pixel(h, v);
-            }
+                        v[c] = sample[c];
+                    if (NC == 3 && transform != 0)
+                    {
+                        color_forward(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
+                    }
+                    else if (mask_needed)
+                    {
+#pragma unroll
+                        for (int32_t c = 0; c < NC; ++c)
+                            v[c] &= h.maxval;
+                    }
+                    enc.pixel(h, v);
+                    sample += NC;
+                    --n;
+                } while ((n & 3) != 0); // the group test is the loop condition: no drain test per pixel
+            } while (n != 0);
         }
         __syncwarp(); // everybody is done with this buffer before the copy two tiles ahead overwrites it
     }
@@ -192,6 +203,9 @@ __global__ void __launch_bounds__(fast_block_threads)
     const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
     for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
         context_lut[i] = context_lut_entry(p, i);
+    __shared__ uint32_t reciprocal_lut[reciprocal_lut_capacity]; // the host only picks this kernel when RESET <= 64
+    for (int32_t i = threadIdx.x; i < reciprocal_lut_capacity; i += fast_block_threads)
+        reciprocal_lut[i] = reciprocal_lut_entry(i);
     __syncthreads();
 
     const ScanJob& job = jobs[blockIdx.y];
@@ -221,6 +235,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.context_lut = context_lut;
     h.context_lut_last = lut_last;
     h.context_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(context_lut));
+    h.reciprocal_lut = reciprocal_lut;
+    h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     FastLineDecoder<NC, LOSSLESS, true> dec;
     const uint8_t* stream = job.stream_in;
@@ -248,20 +264,24 @@ __global__ void __launch_bounds__(fast_block_threads)
             int32_t n = width - x0 - beyond;
             do
             {
-                if ((n & (refill_cadence - 1)) == 0)
-                    dec.top_up();
-                dec.pixel(h, beyond + n);
-                int32_t v[NC];
+                dec.top_up(); // at the start of every group of refill_cadence pixels
+#pragma unroll 1
+                do
+                {
+                    dec.pixel(h, beyond, n);
+                    int32_t v[NC];
 #pragma unroll
-                for (int32_t c = 0; c < NC; ++c)
-                    v[c] = dec.ra[c];
-                if (NC == 3 && transform != 0)
-                    color_inverse(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
+                    for (int32_t c = 0; c < NC; ++c)
+                        v[c] = dec.ra[c];
+                    if (NC == 3 && transform != 0)
+                        color_inverse(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
 #pragma unroll
-                for (int32_t c = 0; c < NC; ++c)
-                    sample[c] = static_cast<S>(v[c]);
-                sample += NC;
-            } while (--n != 0);
+                    for (int32_t c = 0; c < NC; ++c)
+                        sample[c] = static_cast<S>(v[c]);
+                    sample += NC;
+                    --n;
+                } while ((n & (refill_cadence - 1)) != 0); // the group test is the loop condition: no top-up test per pixel
+            } while (n != 0);
         }
         __syncwarp();
         tile_store<TW>(tile, pixels, stride, first_line, row_mask, row_bytes, t, lane);
@@ -740,7 +760,7 @@ size_t tiled_dynamic_shared_bytes(const CodecParams& p)
 bool rows_tileable(const CodecParams& p, bool rows_word_aligned)
 {
     const size_t samples_per_pixel = p.interleave == ilv_sample ? static_cast<size_t>(p.components) : 1U;
-    return rows_word_aligned && p.interleave != ilv_line && p.t3 < context_lut_capacity &&
+    return rows_word_aligned && p.interleave != ilv_line && p.t3 < context_lut_capacity && p.reset < reciprocal_lut_capacity &&
            (static_cast<size_t>(p.width) * samples_per_pixel * static_cast<size_t>(p.sample_bytes)) % 4U == 0;
 }
 

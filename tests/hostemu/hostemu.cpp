@@ -16,7 +16,18 @@ namespace {
 // both it and the compare chain are checked against the oracle in every multi-line test.
 bool use_lut(const CodecParams& p, uint32_t interval)
 {
-    return p.t3 < context_lut_capacity && (interval & 1U) != 0;
+    return p.t3 < context_lut_capacity && p.reset < reciprocal_lut_capacity && (interval & 1U) != 0;
+}
+
+const uint32_t* reciprocals()
+{
+    static const std::vector<uint32_t> table = [] {
+        std::vector<uint32_t> t(reciprocal_lut_capacity);
+        for (int32_t i = 0; i < reciprocal_lut_capacity; ++i)
+            t[static_cast<size_t>(i)] = reciprocal_lut_entry(i);
+        return t;
+    }();
+    return table.data();
 }
 
 std::vector<uint8_t> make_lut(const CodecParams& p)
@@ -30,6 +41,25 @@ std::vector<uint8_t> make_lut(const CodecParams& p)
 } // namespace
 
 extern "C" {
+
+// Exhaustive check of the table form of the Golomb parameter against the definition (min k with (n << k) >= a) for
+// n in [1, n_last], a in [0, a_end); returns the number of mismatches.
+uint64_t hostemu_check_golomb_parameter(int32_t n_last, int32_t a_end)
+{
+    uint64_t mismatches = 0;
+    for (int32_t n = 1; n <= n_last; ++n)
+    {
+        const uint32_t reciprocal = reciprocal_lut_entry(n);
+        int32_t k = 0;
+        for (int32_t a = 0; a < a_end; ++a)
+        {
+            while ((static_cast<int64_t>(n) << k) < a)
+                ++k; // the definition, incrementally (k only grows with a)
+            mismatches += golomb_parameter_reciprocal(a, reciprocal) != k || golomb_parameter(a, n) != k;
+        }
+    }
+    return mismatches;
+}
 
 // returns 0 on success
 int hostemu_make_params(CodecParams* out, int32_t width, int32_t height, int32_t bits, int32_t components, int32_t near_lossless,
@@ -71,8 +101,8 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
         if (fast)
         {
 #define HOSTEMU_ENCODE(NC, LL, LINE)                                                                                       \
-    (use_lut(p, i) ? (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data()) \
-                                          : encode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data()))   \
+    (use_lut(p, i) ? (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data(), reciprocals()) \
+                                          : encode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data(), reciprocals()))   \
                    : (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1, slot_bytes)                   \
                                           : encode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1, slot_bytes)))
             if (p.interleave == ilv_sample && p.components == 2)
@@ -167,8 +197,8 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
         if (fast)
         {
 #define HOSTEMU_DECODE(NC, LL, LINE)                                                                                       \
-    (use_lut(p, i) ? (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, lut.data()) \
-                                          : decode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, lut.data()))   \
+    (use_lut(p, i) ? (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, lut.data(), reciprocals()) \
+                                          : decode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, lut.data(), reciprocals()))   \
                    : (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1)                   \
                                           : decode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1)))
             if (p.interleave == ilv_sample && p.components == 2)

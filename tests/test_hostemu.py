@@ -118,3 +118,15 @@ def test_random_parameters(oracle, hostemu, seed):
         gen = rng.choice([s_smooth, s_noise, s_mixed])
         img = gen(h, w, bits, cc, seed=rng.randrange(1 << 30), layout="interleaved") if cc > 1 else gen(h, w, bits, seed=rng.randrange(1 << 30))
         check_scan(oracle, hostemu, img, bits, cc, near, ilv, xf, ri, pc)
+
+
+def test_golomb_parameter_table_form_is_exact(hostemu):
+    """The tile kernels compute k from ceil(2^31 / N) (jls_fast.cuh: golomb_parameter_reciprocal).  Exhaustive against
+    the definition -- min k with (N << k) >= A, reference src/regular_mode_context.hpp:99-111 -- for every N the kernels
+    use it for (N <= RESET <= 64) and every A below the reference's sanity bound 2^24 (:52-54), A = 0 included."""
+    import ctypes
+
+    check = hostemu.dll.hostemu_check_golomb_parameter
+    check.restype = ctypes.c_uint64
+    check.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    assert check(64, 1 << 24) == 0
