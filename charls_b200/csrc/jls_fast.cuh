@@ -630,9 +630,20 @@ JLS_HD int32_t fast_decode_run_length(FastReader& br, int32_t& run_index, int32_
 // ---------------------------------------------------------------------------------------------------------------------
 // Per-line state shared by encoder and decoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool USE_LUT>
+// LUT_MODE: lut_none = compare chain and count-leading-zeros forms; lut_clamped = tables, the context table covers
+// Ra in [0, context_lut_last] and larger Ra take its last entry; lut_full = the context table covers every sample value
+// (8-bit containers: 256 entries), no clamp.  `true` / `false` select lut_clamped / lut_none.
+enum : int
+{
+    lut_none = 0,
+    lut_clamped = 1,
+    lut_full = 2
+};
+
+template<int NC, int LUT_MODE>
 struct FastLineState
 {
+    static constexpr bool USE_LUT = LUT_MODE != lut_none;
     RegularContext* contexts; // this thread's context q lives at contexts[q * context_stride] (device: shared memory)
     int32_t context_stride;
 #if defined(__CUDA_ARCH__)
@@ -756,10 +767,11 @@ struct FastLineState
         {
 #if defined(__CUDA_ARCH__)
             uint32_t q;
-            asm("ld.shared.u8 %0, [%1];" : "=r"(q) : "r"(h.context_lut_shared + static_cast<uint32_t>(imin(ra_value, h.context_lut_last))));
+            const int32_t index = LUT_MODE == lut_full ? ra_value : imin(ra_value, h.context_lut_last);
+            asm("ld.shared.u8 %0, [%1];" : "=r"(q) : "r"(h.context_lut_shared + static_cast<uint32_t>(index)));
             return static_cast<int32_t>(q);
 #else
-            return h.context_lut[imin(ra_value, h.context_lut_last)];
+            return h.context_lut[LUT_MODE == lut_full ? ra_value : imin(ra_value, h.context_lut_last)];
 #endif
         }
         return context_index_compare(h, ra_value);
@@ -780,8 +792,8 @@ struct FastLineState
 // ---------------------------------------------------------------------------------------------------------------------
 // Encoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS, bool USE_LUT = false, bool DEFERRED = true>
-struct FastLineEncoder : FastLineState<NC, USE_LUT>
+template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, bool DEFERRED = true>
+struct FastLineEncoder : FastLineState<NC, LUT_MODE>
 {
     FastWriter bw;
     int32_t run_count;
@@ -795,14 +807,14 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
 
     JLS_HD void begin_line()
     {
-        FastLineState<NC, USE_LUT>::begin_line();
+        FastLineState<NC, LUT_MODE>::begin_line();
         run_count = 0;
     }
 
     // regular mode for one sample (reference src/scan_encoder_core.hpp:40-55); prediction = Ra, sign < 0 unless q == 0
     JLS_HD int32_t regular(const HotParams& h, int32_t x, int32_t ra_value)
     {
-        const int32_t q = FastLineState<NC, USE_LUT>::context_index(h, ra_value);
+        const int32_t q = FastLineState<NC, LUT_MODE>::context_index(h, ra_value);
         this->select_context(h, q);
         RegularContext& c = this->cached;
         const int32_t k = this->golomb_k();
@@ -891,8 +903,8 @@ struct FastLineEncoder : FastLineState<NC, USE_LUT>
 // ---------------------------------------------------------------------------------------------------------------------
 // Decoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS, bool USE_LUT = false>
-struct FastLineDecoder : FastLineState<NC, USE_LUT>
+template<int NC, bool LOSSLESS, int LUT_MODE = lut_none>
+struct FastLineDecoder : FastLineState<NC, LUT_MODE>
 {
     FastReader br;
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
@@ -915,21 +927,24 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
 
     JLS_HD void begin_line()
     {
-        FastLineState<NC, USE_LUT>::begin_line();
+        FastLineState<NC, LUT_MODE>::begin_line();
         pending = 0;
     }
 
     // reference src/scan_decoder_core.hpp:38-69
     JLS_HD int32_t regular(const HotParams& h, int32_t ra_value)
     {
-        const int32_t q = FastLineState<NC, USE_LUT>::context_index(h, ra_value);
+        const int32_t q = FastLineState<NC, LUT_MODE>::context_index(h, ra_value);
         this->select_context(h, q);
         RegularContext& c = this->cached;
         const bool negative = NC == 1 || q != 0;
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
         const int32_t k = this->golomb_k();
         const bool flip = k == 0 && (LOSSLESS || h.near == 0) && 2 * c.b + c.n < 1; // see the encoder
-        const int32_t e = unmap_error_value(br.get_golomb_steady(h, k, h.escape) ^ (flip ? 1 : 0));
+        // unmap(m ^ 1) == ~unmap(m): the correction becomes one predicated complement behind the unmapping
+        int32_t e = unmap_error_value(br.get_golomb_steady(h, k, h.escape));
+        if (flip)
+            e = ~e;
         // The reference's sanity checks -- k >= 16 (src/regular_mode_context.hpp:107-108), |e| > 65535
         // (src/scan_decoder_core.hpp:57-58) and the context's (:52-54) -- without branches or clamps: each quantity is
         // scaled so that its bound is sanity_limit and goes into a running maximum.  k <= 31 and |e| < 2^22 on every
@@ -998,7 +1013,9 @@ struct FastLineDecoder : FastLineState<NC, USE_LUT>
     // is needed on the run-mode path only and is formed there).
     JLS_HD void pixel(const HotParams& h, int32_t remaining_a, int32_t remaining_b)
     {
-        if (JLS_UNLIKELY((pending != 0) | this->in_run_mode(h)))
+        // `pending != 0` implies run mode (Ra stays at the value that started the run until the interruption sample is
+        // decoded), so one test covers the pixels of a run, its interruption sample and the start of a run
+        if (JLS_UNLIKELY(this->in_run_mode(h)))
         {
             run_mode_pixel(h, remaining_a + remaining_b);
             return;

@@ -85,7 +85,7 @@ JLS_HD void fast_store_pixel(const CodecParams& p, S* line, int32_t x, const int
 // LINE_ILV: the interval holds one line of each of p.components components (line interleave); NC must be 1 then.
 // USE_LUT: context_lut holds context_lut_entry(p, 0 .. min(T3, capacity - 1)), reciprocal_lut holds
 // reciprocal_lut_entry(0 .. RESET) (RESET < reciprocal_lut_capacity).
-template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, bool USE_LUT = false>
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, int USE_LUT = lut_none>
 JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
                                            RegularContext* contexts, int32_t context_stride, size_t slot_bytes,
                                            const uint8_t* context_lut = nullptr, const uint32_t* reciprocal_lut = nullptr)
@@ -161,7 +161,7 @@ JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool 
     return br.unread_bytes() > 7 ? err_restart_marker_not_found : err_none;
 }
 
-template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, bool USE_LUT = false>
+template<int NC, bool LOSSLESS, typename S, bool LINE_ILV, int USE_LUT = lut_none>
 JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& job, uint32_t interval,
                                            RegularContext* contexts, int32_t context_stride,
                                            const uint8_t* context_lut = nullptr, const uint32_t* reciprocal_lut = nullptr)

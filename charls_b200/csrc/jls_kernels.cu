@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     __shared__ uint32_t tiles[warps][2][32 * SW];
     extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
-    const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
+    // the host only picks this kernel when T3 fits; 8-bit containers get an entry for every sample value (no clamp)
+    const int32_t lut_last = sizeof(S) == 1 ? 255 : min(p.t3, context_lut_capacity - 1);
     for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
         context_lut[i] = context_lut_entry(p, i);
     __shared__ uint32_t reciprocal_lut[reciprocal_lut_capacity]; // the host only picks this kernel when RESET <= 64
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
-    FastLineEncoder<NC, LOSSLESS, true, !(LOSSLESS && sizeof(S) == 2)> enc;
+    FastLineEncoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, !(LOSSLESS && sizeof(S) == 2)> enc;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts + threadIdx.x, fast_block_threads, slot);
@@ -195,12 +196,13 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
     // pixels between two top-ups of the 128-bit read window (see FastReader::get_golomb_steady)
-    constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, false>::pixels_per_top_up;
+    constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, lut_none>::pixels_per_top_up;
     __shared__ RegularContext contexts[5 * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
     extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
-    const int32_t lut_last = min(p.t3, context_lut_capacity - 1); // the host only picks this kernel when T3 fits
+    // the host only picks this kernel when T3 fits; 8-bit containers get an entry for every sample value (no clamp)
+    const int32_t lut_last = sizeof(S) == 1 ? 255 : min(p.t3, context_lut_capacity - 1);
     for (int32_t i = threadIdx.x; i <= lut_last; i += fast_block_threads)
         context_lut[i] = context_lut_entry(p, i);
     __shared__ uint32_t reciprocal_lut[reciprocal_lut_capacity]; // the host only picks this kernel when RESET <= 64
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.reciprocal_lut = reciprocal_lut;
     h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
-    FastLineDecoder<NC, LOSSLESS, true> dec;
+    FastLineDecoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
     dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
@@ -744,11 +746,12 @@ cudaError_t launch_with_shared(Kernel kernel, dim3 grid, dim3 block, size_t dyna
     return cudaGetLastError();
 }
 
-// The tile kernels keep the context-index table |Q(-Ra)|, Ra = 0 .. min(T3, capacity - 1), in dynamic shared memory: 22
-// bytes for 8-bit defaults, 277 for 12..16 bit.  A fixed 1 KB table per one-warp block costs three resident blocks per SM.
+// The tile kernels keep the context-index table |Q(-Ra)| in dynamic shared memory: Ra = 0 .. 255 for 8-bit containers (no
+// clamp in the pixel loop), Ra = 0 .. min(T3, capacity - 1) otherwise (277 bytes for the 12..16 bit defaults).  A fixed 1 KB table per one-warp block costs three resident blocks per SM.
 size_t tiled_dynamic_shared_bytes(const CodecParams& p)
 {
-    const size_t entries = static_cast<size_t>(p.t3 < context_lut_capacity - 1 ? p.t3 : context_lut_capacity - 1) + 1;
+    const size_t entries =
+        p.sample_bytes == 1 ? 256U : static_cast<size_t>(p.t3 < context_lut_capacity - 1 ? p.t3 : context_lut_capacity - 1) + 1;
     return (entries + 15) / 16 * 16;
 }
 

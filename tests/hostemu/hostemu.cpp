@@ -33,7 +33,7 @@ const uint32_t* reciprocals()
 std::vector<uint8_t> make_lut(const CodecParams& p)
 {
     std::vector<uint8_t> lut(context_lut_capacity, 0);
-    for (int32_t i = 0; i <= std::min(p.t3, context_lut_capacity - 1); ++i)
+    for (int32_t i = 0; i <= std::max(std::min(p.t3, context_lut_capacity - 1), 255); ++i) // 8-bit containers: every value
         lut[static_cast<size_t>(i)] = context_lut_entry(p, i);
     return lut;
 }
@@ -102,7 +102,7 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
         {
 #define HOSTEMU_ENCODE(NC, LL, LINE)                                                                                       \
     (use_lut(p, i) ? (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data(), reciprocals()) \
-                                          : encode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, slot_bytes, lut.data(), reciprocals()))   \
+                                          : encode_interval_fast<NC, LL, uint8_t, LINE, lut_full>(p, job, i, contexts, 1, slot_bytes, lut.data(), reciprocals()))   \
                    : (p.sample_bytes == 2 ? encode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1, slot_bytes)                   \
                                           : encode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1, slot_bytes)))
             if (p.interleave == ilv_sample && p.components == 2)
@@ -198,7 +198,7 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
         {
 #define HOSTEMU_DECODE(NC, LL, LINE)                                                                                       \
     (use_lut(p, i) ? (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE, true>(p, job, i, contexts, 1, lut.data(), reciprocals()) \
-                                          : decode_interval_fast<NC, LL, uint8_t, LINE, true>(p, job, i, contexts, 1, lut.data(), reciprocals()))   \
+                                          : decode_interval_fast<NC, LL, uint8_t, LINE, lut_full>(p, job, i, contexts, 1, lut.data(), reciprocals()))   \
                    : (p.sample_bytes == 2 ? decode_interval_fast<NC, LL, uint16_t, LINE>(p, job, i, contexts, 1)                   \
                                           : decode_interval_fast<NC, LL, uint8_t, LINE>(p, job, i, contexts, 1)))
             if (p.interleave == ilv_sample && p.components == 2)
