@@ -528,48 +528,73 @@ __device__ __forceinline__ MarkerChunk marker_chunk(const uint8_t* data, size_t 
     return chunk;
 }
 
-// grid (blocks, jobs): block_counts[job][block]
+// Every block covers marker_sections sections of marker_bytes_per_block stream bytes: the 16-byte loads of all sections
+// are issued before any of them is used (four independent loads in flight per thread; with one section per block the
+// kernel ran at 2.5 TB/s).  Counts and chunk masks stay per section, so the scan and the layout are those of one section
+// per block.
+#ifndef JLS_MARKER_SECTIONS
+#define JLS_MARKER_SECTIONS 4
+#endif
+constexpr int marker_sections = JLS_MARKER_SECTIONS;
+
+// grid (ceil(sections / marker_sections), jobs): block_counts[job][section]
 __global__ void __launch_bounds__(marker_block_threads)
     k_marker_count(const ScanJob* __restrict__ jobs, uint32_t* __restrict__ block_counts, uint32_t blocks_per_job,
                    uint16_t* __restrict__ chunk_masks)
 {
     const ScanJob& job = jobs[blockIdx.y];
-    const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
-    uint32_t mask;
-    const int64_t base = marker_chunk_base(job.stream_in, chunk_index);
-    const bool interior = base >= 1 && base + marker_bytes_per_thread <= static_cast<int64_t>(job.stream_in_size);
-    if (__all_sync(0xFFFFFFFFU, interior))
-    {
-        // the whole warp reads 512 consecutive stream bytes: a lane's preceding byte is its neighbour's last one
-        const uint8_t* data = job.stream_in;
-        assume_global(data);
-        const uint4 q = *reinterpret_cast<const uint4*>(data + base);
-        uint32_t previous = __shfl_up_sync(0xFFFFFFFFU, q.w >> 24, 1);
-        if ((threadIdx.x & 31) == 0)
-            previous = data[base - 1];
-        mask = marker_mask_of(q, previous);
-    }
-    else
-    {
-        mask = marker_chunk(job.stream_in, job.stream_in_size, chunk_index).mask;
-    }
-    // kept for k_marker_write: 2 bytes per 16 stream bytes instead of a second pass over the stream
-    chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index] = static_cast<uint16_t>(mask);
-    const uint32_t count = __popc(mask);
-    __shared__ uint32_t warp_sums[marker_block_threads / 32];
-    uint32_t sum = count;
+    const uint8_t* data = job.stream_in;
+    assume_global(data);
+    const uint32_t first_section = blockIdx.x * marker_sections;
+    uint4 q[marker_sections];
+    bool fast[marker_sections];
 #pragma unroll
-    for (int delta = 16; delta > 0; delta >>= 1)
-        sum += __shfl_down_sync(0xFFFFFFFFU, sum, delta);
-    if ((threadIdx.x & 31) == 0)
-        warp_sums[threadIdx.x >> 5] = sum;
+    for (int s = 0; s < marker_sections; ++s)
+    {
+        const size_t chunk_index = static_cast<size_t>(first_section + s) * marker_block_threads + threadIdx.x;
+        const int64_t base = marker_chunk_base(data, chunk_index);
+        const bool interior = base >= 1 && base + marker_bytes_per_thread <= static_cast<int64_t>(job.stream_in_size);
+        // the whole warp reads 512 consecutive stream bytes: a lane's preceding byte is its neighbour's last one
+        fast[s] = __all_sync(0xFFFFFFFFU, interior);
+        if (fast[s])
+            q[s] = *reinterpret_cast<const uint4*>(data + base);
+    }
+    __shared__ uint32_t warp_sums[marker_sections][marker_block_threads / 32];
+#pragma unroll
+    for (int s = 0; s < marker_sections; ++s)
+    {
+        const uint32_t section = first_section + s;
+        if (section >= blocks_per_job)
+            break; // whole block
+        const size_t chunk_index = static_cast<size_t>(section) * marker_block_threads + threadIdx.x;
+        uint32_t mask;
+        if (fast[s])
+        {
+            uint32_t previous = __shfl_up_sync(0xFFFFFFFFU, q[s].w >> 24, 1);
+            if ((threadIdx.x & 31) == 0)
+                previous = data[marker_chunk_base(data, chunk_index) - 1];
+            mask = marker_mask_of(q[s], previous);
+        }
+        else
+        {
+            mask = marker_chunk(data, job.stream_in_size, chunk_index).mask;
+        }
+        // kept for k_marker_write: 2 bytes per 16 stream bytes instead of a second pass over the stream
+        chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index] = static_cast<uint16_t>(mask);
+        uint32_t sum = __popc(mask);
+#pragma unroll
+        for (int delta = 16; delta > 0; delta >>= 1)
+            sum += __shfl_down_sync(0xFFFFFFFFU, sum, delta);
+        if ((threadIdx.x & 31) == 0)
+            warp_sums[s][threadIdx.x >> 5] = sum;
+    }
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x < marker_sections && first_section + threadIdx.x < blocks_per_job)
     {
         uint32_t block_sum = 0;
         for (int w = 0; w < marker_block_threads / 32; ++w)
-            block_sum += warp_sums[w];
-        block_counts[static_cast<size_t>(blockIdx.y) * blocks_per_job + blockIdx.x] = block_sum;
+            block_sum += warp_sums[threadIdx.x][w];
+        block_counts[static_cast<size_t>(blockIdx.y) * blocks_per_job + first_section + threadIdx.x] = block_sum;
     }
 }
 
@@ -595,57 +620,74 @@ __global__ void __launch_bounds__(scan_block_threads)
 }
 
 // Writes interval_offset[2i] / [2i+1] (begin / end of interval i) for the first interval_count markers and remembers
-// each marker's code in marker_codes[job][i].
+// each marker's code in marker_codes[job][i].  Sections per block as in k_marker_count.
 __global__ void __launch_bounds__(marker_block_threads)
     k_marker_write(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
                    const uint32_t* __restrict__ block_counts, uint32_t blocks_per_job, uint8_t* __restrict__ marker_codes,
                    const uint16_t* __restrict__ chunk_masks)
 {
-    __shared__ uint32_t warp_sums[marker_block_threads / 32];
+    __shared__ uint32_t warp_sums[marker_sections][marker_block_threads / 32];
     const ScanJob& job = jobs[blockIdx.y];
-    const size_t chunk_index = static_cast<size_t>(blockIdx.x) * marker_block_threads + threadIdx.x;
     assume_global(job.stream_in);
-    MarkerChunk chunk;
-    chunk.base = marker_chunk_base(job.stream_in, chunk_index);
-    chunk.mask = chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index];
-    const uint32_t mask = chunk.mask;
-    const uint32_t count = __popc(mask);
+    const uint32_t first_section = blockIdx.x * marker_sections;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inclusive = count;
+    uint32_t masks[marker_sections], inclusive[marker_sections];
 #pragma unroll
-    for (int delta = 1; delta < 32; delta <<= 1)
+    for (int s = 0; s < marker_sections; ++s)
     {
-        const uint32_t other = __shfl_up_sync(0xFFFFFFFFU, inclusive, delta);
-        if (lane >= delta)
-            inclusive += other;
+        const size_t chunk_index = static_cast<size_t>(first_section + s) * marker_block_threads + threadIdx.x;
+        masks[s] = first_section + s < blocks_per_job
+                       ? chunk_masks[static_cast<size_t>(blockIdx.y) * blocks_per_job * marker_block_threads + chunk_index]
+                       : 0U;
     }
-    if (lane == 31)
-        warp_sums[warp] = inclusive;
+#pragma unroll
+    for (int s = 0; s < marker_sections; ++s)
+    {
+        inclusive[s] = __popc(masks[s]);
+#pragma unroll
+        for (int delta = 1; delta < 32; delta <<= 1)
+        {
+            const uint32_t other = __shfl_up_sync(0xFFFFFFFFU, inclusive[s], delta);
+            if (lane >= delta)
+                inclusive[s] += other;
+        }
+        if (lane == 31)
+            warp_sums[s][warp] = inclusive[s];
+    }
     __syncthreads();
-    uint32_t rank = block_counts[static_cast<size_t>(blockIdx.y) * blocks_per_job + blockIdx.x] + inclusive - count;
-    for (int w = 0; w < warp; ++w)
-        rank += warp_sums[w];
     if (threadIdx.x == 0 && blockIdx.x == 0)
         job.interval_offset[0] = 0;
 
-    uint32_t remaining = mask;
-    while (remaining != 0 && rank < p.interval_count)
+#pragma unroll
+    for (int s = 0; s < marker_sections; ++s)
     {
-        const uint32_t bit = __ffs(remaining) - 1;
-        remaining &= remaining - 1;
-        const size_t code_position = static_cast<size_t>(chunk.base + bit);
-        size_t marker_begin = code_position - 1;
-        while (marker_begin > 0 && job.stream_in[marker_begin - 1] == 0xFF) // fill bytes (T.81 B.1.1.2)
-            --marker_begin;
-        job.interval_offset[2 * static_cast<size_t>(rank) + 1] = marker_begin;
-        if (rank + 1 < p.interval_count)
-            job.interval_offset[2 * static_cast<size_t>(rank) + 2] = code_position + 1;
-        const uint8_t code = job.stream_in[code_position];
-        marker_codes[static_cast<size_t>(blockIdx.y) * p.interval_count + rank] = code;
-        // the first interval_count - 1 markers must be RSTm with m = index mod 8 (reference src/scan_decoder.hpp:335-349)
-        if (rank + 1 < p.interval_count && code != 0xD0U + (rank & 7U))
-            report_error(job, rank, err_restart_marker_not_found);
-        ++rank;
+        uint32_t remaining = masks[s];
+        if (remaining == 0)
+            continue;
+        const size_t chunk_index = static_cast<size_t>(first_section + s) * marker_block_threads + threadIdx.x;
+        const int64_t chunk_base = marker_chunk_base(job.stream_in, chunk_index);
+        uint32_t rank = block_counts[static_cast<size_t>(blockIdx.y) * blocks_per_job + first_section + s] + inclusive[s] -
+                        __popc(remaining);
+        for (int w = 0; w < warp; ++w)
+            rank += warp_sums[s][w];
+        while (remaining != 0 && rank < p.interval_count)
+        {
+            const uint32_t bit = __ffs(remaining) - 1;
+            remaining &= remaining - 1;
+            const size_t code_position = static_cast<size_t>(chunk_base + bit);
+            size_t marker_begin = code_position - 1;
+            while (marker_begin > 0 && job.stream_in[marker_begin - 1] == 0xFF) // fill bytes (T.81 B.1.1.2)
+                --marker_begin;
+            job.interval_offset[2 * static_cast<size_t>(rank) + 1] = marker_begin;
+            if (rank + 1 < p.interval_count)
+                job.interval_offset[2 * static_cast<size_t>(rank) + 2] = code_position + 1;
+            const uint8_t code = job.stream_in[code_position];
+            marker_codes[static_cast<size_t>(blockIdx.y) * p.interval_count + rank] = code;
+            // the first interval_count - 1 markers must be RSTm with m = index mod 8 (reference src/scan_decoder.hpp:335-349)
+            if (rank + 1 < p.interval_count && code != 0xD0U + (rank & 7U))
+                report_error(job, rank, err_restart_marker_not_found);
+            ++rank;
+        }
     }
 }
 
@@ -935,11 +977,12 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
                    device_jobs));
     uint16_t* chunk_masks =
         reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(block_counts) + marker_counts_bytes(job_count, blocks_per_job));
-    JLS_TRY(launch(k_marker_count, dim3(blocks_per_job, job_count), dim3(marker_block_threads), stream, device_jobs,
+    const uint32_t marker_grid = (blocks_per_job + marker_sections - 1) / marker_sections;
+    JLS_TRY(launch(k_marker_count, dim3(marker_grid, job_count), dim3(marker_block_threads), stream, device_jobs,
                    block_counts, blocks_per_job, chunk_masks));
     JLS_TRY(launch(k_marker_scan, dim3(job_count), dim3(scan_block_threads), stream, block_counts, blocks_per_job,
                    marker_totals));
-    JLS_TRY(launch(k_marker_write, dim3(blocks_per_job, job_count), dim3(marker_block_threads), stream, p, device_jobs,
+    JLS_TRY(launch(k_marker_write, dim3(marker_grid, job_count), dim3(marker_block_threads), stream, p, device_jobs,
                    static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes,
                    static_cast<const uint16_t*>(chunk_masks)));
 

@@ -440,3 +440,92 @@ def test_page_locked_destination(product, oracle, direct, monkeypatch):
                 enc.encode(image)
         assert info.value.errc == 3
         assert (short.numpy()[len(want) - 9 :] == 0x5A).all(), case
+
+
+# -- frames coded scan by scan (reference test/encode_test.cpp:430-553) ---------------------------------------------------
+
+
+def encode_scan_by_scan(lib, w, h, bits, component_count, scans, restart_interval=None):
+    """scans: (pixels, source_component_count, interleave_mode, near, preset or None) per encode_components call."""
+    from charls_b200.codec import JpegLSEncoder
+
+    with JpegLSEncoder(lib) as enc:
+        enc.frame_info(w, h, bits, component_count)
+        if restart_interval is not None and lib.has_extensions:
+            enc.restart_interval(restart_interval)
+        dst = np.empty(enc.estimated_destination_size() * 2 + 4096, dtype=np.uint8)
+        enc.destination(dst)
+        n = 0
+        for pixels, count, ilv, near, preset in scans:
+            enc.interleave_mode(ilv).near_lossless(near)
+            enc.preset_coding_parameters(*(preset or (0, 0, 0, 0, 0)))
+            n = enc.encode_components(np.ascontiguousarray(pixels), count)
+        return dst[:n].tobytes()
+
+
+def decode_with_scan_getters(lib, stream, component_count):
+    from charls_b200.codec import JpegLSDecoder
+
+    with JpegLSDecoder(lib) as dec:
+        dec.source(stream).read_header()
+        raw = dec.decode()
+        return raw.tobytes(), [(dec.near_lossless(c), dec.interleave_mode(c)) for c in range(component_count)]
+
+
+def mixed_scan_cases():
+    rng = np.random.default_rng(99)
+    for (w, h, bits) in ((8, 2, 8), (157, 43, 8), (96, 40, 12)):
+        dtype = np.uint8 if bits <= 8 else np.dtype("<u2")
+        plane = lambda k: s_mixed(h, w, bits, seed=10 + k).astype(dtype)  # noqa: E731
+        triple = np.stack([plane(1), plane(2), plane(3)], axis=-1)
+        pair = np.stack([plane(4), plane(5)], axis=-1)
+        mx = (1 << bits) - 1
+        # three scans of one component with NEAR 0 / 2 / 10 (encode_test.cpp:430-457)
+        yield "near per scan", w, h, bits, 3, [(plane(0), 1, 0, 0, None), (plane(1), 1, 0, 2, None), (plane(2), 1, 0, 10, None)]
+        # different preset coding parameters per scan (:459-484)
+        yield "preset per scan", w, h, bits, 3, [(plane(0), 1, 0, 0, None), (plane(1), 1, 0, 0, (mx, 10, 20, 22, 64)),
+                                                  (plane(2), 1, 0, 0, (mx, 0, 0, 0, 3))]
+        # ILV none first, then a sample-interleaved scan of three (:486-517) and the other way round (:519-553)
+        yield "none then sample", w, h, bits, 4, [(plane(0), 1, 0, 0, None), (triple, 3, 2, 0, None)]
+        yield "sample then none", w, h, bits, 4, [(triple, 3, 2, int(rng.integers(0, 3)), None), (plane(0), 1, 0, 0, None)]
+        yield "line pair, sample pair", w, h, bits, 4, [(pair, 2, 1, 1, None), (pair[:, ::-1].copy(), 2, 2, 0, None)]
+
+
+def test_frames_coded_scan_by_scan(product, oracle):
+    """encode_components with interleave mode, NEAR and preset parameters changing from scan to scan: without restart
+    markers the stream is the reference's byte for byte; with them the reference decodes it to the pixels and per-scan
+    getters our decoder reports (reference src/charls_jpegls_encoder.cpp:187-236, test/encode_test.cpp:430-553)."""
+    reference = reference_library() if have_reference_build() else None
+    for name, w, h, bits, cc, scans in mixed_scan_cases():
+        tag = (name, w, h, bits)
+        plain = encode_scan_by_scan(product, w, h, bits, cc, scans, restart_interval=0)
+        marked = encode_scan_by_scan(product, w, h, bits, cc, scans, restart_interval=1)
+        parsed = jlsio.parse(marked)
+        assert [sc.component_count for sc in parsed.scans] == [count for _, count, _, _, _ in scans], tag
+        # every scan's payload is what the oracle writes for that scan alone
+        first = 0
+        for sc, (pixels, count, ilv, near, preset) in zip(parsed.scans, scans):
+            p = oracle.params(w, h, bits, count, near, ilv, 0, preset, 1)
+            assert marked[sc.data_offset : sc.data_end] == oracle.encode_scan(p, np.ascontiguousarray(pixels)), tag + (first,)
+            first += count
+        want_getters = [(near, ilv) for _, count, ilv, near, _ in scans for _ in range(count)]
+        decoded = {}
+        for ri, stream in ((0, plain), (1, marked)):
+            # near-lossless reconstruction depends on the restart interval: the oracle decodes what it coded the same way
+            expected = b"".join(oracle_reconstruction(oracle, w, h, bits, *scan, ri) for scan in scans)
+            decoded[ri] = decode_with_scan_getters(product, stream, cc)
+            assert decoded[ri] == (expected, want_getters), tag + (ri,)
+        if reference is not None:
+            assert plain == encode_scan_by_scan(reference, w, h, bits, cc, scans), tag
+            assert decode_with_scan_getters(reference, marked, cc) == decoded[1], tag
+            assert decode_with_scan_getters(reference, plain, cc) == decoded[0], tag
+
+
+def oracle_reconstruction(oracle, w, h, bits, pixels, count, ilv, near, preset, ri):
+    pixels = np.ascontiguousarray(pixels)
+    if near == 0:
+        return pixels.tobytes()
+    p = oracle.params(w, h, bits, count, near, ilv, 0, preset, ri)
+    out = np.zeros_like(pixels)
+    assert oracle.decode_scan(p, oracle.encode_scan(p, pixels) + b"\xff\xd9", out) > 0
+    return out.tobytes()
