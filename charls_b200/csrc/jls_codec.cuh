@@ -709,54 +709,45 @@ JLS_HD int32_t decode_regular_sample(const CodecParams& p, BitReader& br, Regula
 // ---------------------------------------------------------------------------------------------------------------------
 JLS_HD void color_forward(int32_t transform, int32_t type_mask, int32_t& c0, int32_t& c1, int32_t& c2)
 {
+    // transform is 1, 2 or 3 (the host validates it).  HP1 on its own path, HP2 / HP3 as selects: a chain of equality
+    // tests on `transform` becomes a jump table (an indirect branch per pixel in the tile kernels).
     const int32_t range = type_mask + 1, bias = range / 2;
     const int32_t r = c0, g = c1, b = c2;
+    const int32_t r_g = (r - g + bias) & type_mask;
+    const int32_t b_g = (b - g + bias) & type_mask;
     if (transform == 1)
     {
-        c0 = (r - g + bias) & type_mask;
+        c0 = r_g;
         c1 = g & type_mask;
-        c2 = (b - g + bias) & type_mask;
+        c2 = b_g;
+        return;
     }
-    else if (transform == 2)
-    {
-        c0 = (r - g + bias) & type_mask;
-        c1 = g & type_mask;
-        c2 = (b - ((r + g) >> 1) + bias) & type_mask; // r, g >= 0: division == shift
-    }
-    else if (transform == 3)
-    {
-        const int32_t v2 = (b - g + bias) & type_mask;
-        const int32_t v3 = (r - g + bias) & type_mask;
-        c0 = (g + ((v2 + v3) >> 2) - range / 4) & type_mask;
-        c1 = v2;
-        c2 = v3;
-    }
+    const bool hp3 = transform == 3;
+    const int32_t hp2_c2 = (b - ((r + g) >> 1) + bias) & type_mask; // r, g >= 0: division == shift
+    const int32_t hp3_c0 = (g + ((b_g + r_g) >> 2) - range / 4) & type_mask;
+    c0 = hp3 ? hp3_c0 : r_g;
+    c1 = hp3 ? b_g : (g & type_mask);
+    c2 = hp3 ? r_g : hp2_c2;
 }
 
 JLS_HD void color_inverse(int32_t transform, int32_t type_mask, int32_t& c0, int32_t& c1, int32_t& c2)
 {
     const int32_t range = type_mask + 1, bias = range / 2;
     const int32_t v1 = c0, v2 = c1, v3 = c2;
+    const int32_t r12 = (v1 + v2 - bias) & type_mask; // R of HP1 and HP2
     if (transform == 1)
     {
-        c0 = (v1 + v2 - bias) & type_mask;
+        c0 = r12;
         c1 = v2 & type_mask;
         c2 = (v3 + v2 - bias) & type_mask;
+        return;
     }
-    else if (transform == 2)
-    {
-        const int32_t r = (v1 + v2 - bias) & type_mask;
-        c0 = r;
-        c1 = v2 & type_mask;
-        c2 = (v3 + ((r + (v2 & type_mask)) >> 1) - bias) & type_mask;
-    }
-    else if (transform == 3)
-    {
-        const int32_t g = v1 - ((v3 + v2) >> 2) + range / 4;
-        c0 = (v3 + g - bias) & type_mask;
-        c1 = g & type_mask;
-        c2 = (v2 + g - bias) & type_mask;
-    }
+    const bool hp3 = transform == 3;
+    const int32_t hp2_b = (v3 + ((r12 + (v2 & type_mask)) >> 1) - bias) & type_mask;
+    const int32_t hp3_g = v1 - ((v3 + v2) >> 2) + range / 4;
+    c0 = hp3 ? (v3 + hp3_g - bias) & type_mask : r12;
+    c1 = (hp3 ? hp3_g : v2) & type_mask;
+    c2 = hp3 ? (v2 + hp3_g - bias) & type_mask : hp2_b;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

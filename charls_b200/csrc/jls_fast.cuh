@@ -25,12 +25,16 @@
 #define JLS_LIKELY(x) (x)
 #endif
 
+#ifndef JLS_STUFFED_WORD_PATH
+#define JLS_STUFFED_WORD_PATH 1
+#endif
+
 namespace jls {
 
 // The coding parameters a line needs, held in registers.
 struct HotParams
 {
-    int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init;
+    int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init, transform;
     uint32_t dq_magic;
     uint32_t sign_scale; // 2^(32 - bits)
     // Optional table |Q(-Ra)| for Ra in [0, context_lut_last]; larger Ra use the last entry (they are >= T3).  The tile
@@ -90,6 +94,7 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.range = p.range;
     h.range_dq = p.range_dq;
     h.a_init = p.a_init;
+    h.transform = p.transform;
     h.dq_magic = p.dq_magic;
     h.sign_scale = 1U << (32 - p.bits_per_sample);
     h.context_lut = nullptr;
@@ -121,6 +126,7 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
         scratch[9] = static_cast<int32_t>(h.reciprocal_lut_shared);
         scratch[10] = static_cast<int32_t>(h.sign_scale);
         scratch[11] = h.context_lut_last;
+        scratch[12] = h.transform;
     }
     __syncwarp();
     h.t1 = scratch[0];
@@ -135,8 +141,9 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
     h.reciprocal_lut_shared = static_cast<uint32_t>(scratch[9]);
     h.sign_scale = static_cast<uint32_t>(scratch[10]);
     h.context_lut_last = scratch[11];
+    h.transform = scratch[12];
 }
-constexpr int hot_scratch_words = 12;
+constexpr int hot_scratch_words = 13;
 #endif
 
 template<bool LOSSLESS>
@@ -269,10 +276,51 @@ struct FastWriter
         }
         else
         {
+#if JLS_STUFFED_WORD_PATH
+            flush_word_stuffed(w);
+#else
             do
             {
                 emit_one_stuffed_byte();
             } while (nbits >= 32);
+#endif
+        }
+    }
+
+    // The same word when a 0xFF byte is around: four output bytes again, the byte after a 0xFF takes seven bits, so 28 to
+    // 32 bits leave the accumulator.  Straight-line (five instructions per byte): a warp takes this path whenever ONE of
+    // its lanes meets a 0xFF, at a fifth of all drains for 8-bit data.  Ends with nbits < 32 like the plain path.
+    JLS_HD void flush_word_stuffed(uint32_t w)
+    {
+        for (;;)
+        {
+            uint32_t out = 0;
+            uint32_t ff = prev_ff;
+            int32_t left = 32; // bits of w not yet taken
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int32_t i = 0; i < 4; ++i)
+            {
+                left -= ff ? 7 : 8;
+                const uint32_t b = (w >> left) & (ff ? 0x7FU : 0xFFU);
+                out = (out << 8) | b;
+                ff = (b == 0xFFU) ? 1U : 0U;
+            }
+            prev_ff = ff;
+            *wp++ = bswap32(funnel_r(out, pend, pend_shift));
+            pend = out;
+            nbits -= 32 - left;
+            if (JLS_LIKELY(nbits < 32))
+                return;
+            w = static_cast<uint32_t>(acc >> (nbits - 32)); // up to four stuffed bits stayed behind
+            if ((prev_ff | has_ff_byte(w)) == 0)
+            {
+                *wp++ = bswap32(funnel_r(w, pend, pend_shift));
+                pend = w;
+                nbits -= 32;
+                return;
+            }
         }
     }
 
@@ -411,6 +459,8 @@ struct FastReader
     const uint32_t* wptr; // aligned word that holds the next byte to fetch
     uint32_t cur;         // *wptr
     uint32_t ahead;       // wptr[1], loaded one refill early so that its latency is hidden behind several pixels of work
+                          // (a second word of look-ahead was tried for top-ups that take two words -- 16-bit RGB -- and
+                          // changed nothing there while costing the one-component decoders 2 %: profiles/r1_notes.md)
     uint32_t shift;       // 8 * (offset of the next byte inside *wptr)
 
     static constexpr int32_t full_mark = 96; // a refill appends words while valid <= full_mark

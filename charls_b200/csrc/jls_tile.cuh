@@ -33,30 +33,30 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
 }
 
-// Where lane `lane` starts in a [32 rows][TW words] tile when the warp walks it 32 words at a time (word k * 32 + lane of
-// the tile in the k-th step), and how it moves from one step to the next: TW = 16: same word, two rows down; TW = 24:
-// eight words to the right and one row down, wrapping into one more row.
+// How the warp walks a whole [32 rows][TW words] tile, 32 words per copy instruction (word k * 32 + lane of the tile in
+// step k).  The walk repeats after `period` steps, `rows` rows further down: TW = 16: every step covers two rows;
+// TW = 24: three steps cover four rows.  Per lane that is `period` offsets inside the group (kept in registers) and one
+// base that advances by `rows` rows.  Written as 24 individual steps, each with its own distance to the next, ptxas hoisted
+// all 24 distances out of the tile loop: 120-128 registers for three-component pixels against 64-72 for the others, and
+// 16 resident warps per SM instead of 28.
 template<int TW>
 struct TileWalk
 {
     static_assert(TW == 16 || TW == 24, "tiles are 64 or 96 bytes wide");
-    uint32_t r, w;
-    __device__ __forceinline__ explicit TileWalk(uint32_t lane) : r(lane / TW), w(lane % TW) {}
-    // advances to the next step; returns the distance in words inside the padded shared-memory tile and reports the
-    // distance in global memory as rows (`rows`) and words (`words`, may be negative)
-    __device__ __forceinline__ void step(int32_t& rows, int32_t& words)
+    static constexpr int period = TW == 16 ? 1 : 3;
+    static constexpr int rows = TW == 16 ? 2 : 4;
+    static constexpr int groups = 32 / rows;
+    uint32_t global_offset[period]; // bytes from the group's first row in global memory
+    uint32_t shared_offset[period]; // bytes from the group's first row in the padded shared-memory tile
+    __device__ __forceinline__ TileWalk(uint32_t lane, uint32_t stride)
     {
-        if constexpr (TW == 16)
+#pragma unroll
+        for (int j = 0; j < period; ++j)
         {
-            rows = 2;
-            words = 0;
-        }
-        else
-        {
-            const bool wrap = w + 8U >= TW;
-            rows = wrap ? 2 : 1;
-            words = wrap ? 8 - TW : 8;
-            w = wrap ? w + 8U - TW : w + 8U;
+            const uint32_t index = static_cast<uint32_t>(j) * 32U + lane;
+            const uint32_t r = index / TW, w = index % TW;
+            global_offset[j] = r * stride + w * 4U;
+            shared_offset[j] = (r * (TW + 1) + w) * 4U;
         }
     }
 };
@@ -69,20 +69,22 @@ __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* p
 {
     if (first_line + 31U <= last_line && (tile_index + 1) * (TW * 4) <= row_bytes)
     {
-        // A whole tile (all 32 lines exist, the row does not end inside it): one pointer per lane that is advanced from
-        // step to step, no bounds to test.  The general form below costs ~25 instructions per step for index arithmetic
-        // (profiles/r1_notes.md), this one 4.
-        TileWalk<TW> walk(lane);
-        const uint8_t* source = pixels + static_cast<size_t>(first_line + walk.r) * stride + tile_index * (TW * 4) + walk.w * 4U;
-        unsigned destination = static_cast<unsigned>(__cvta_generic_to_shared(tile + walk.r * (TW + 1) + walk.w));
+        // A whole tile (all 32 lines exist, the row does not end inside it): a base per group of rows and the lane's
+        // offsets inside a group, no bounds to test.  The general form below costs ~25 instructions per step for index
+        // arithmetic (profiles/r1_notes.md), this one 4.
+        const TileWalk<TW> walk(lane, static_cast<uint32_t>(stride));
+        const uint8_t* source = pixels + static_cast<size_t>(first_line) * stride + tile_index * (TW * 4);
+        unsigned destination = static_cast<unsigned>(__cvta_generic_to_shared(tile));
 #pragma unroll
-        for (int k = 0; k < TW; ++k)
+        for (int g = 0; g < TileWalk<TW>::groups; ++g)
         {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(destination), "l"(source) : "memory");
-            int32_t rows, words;
-            walk.step(rows, words);
-            source += static_cast<size_t>(rows) * stride + words * 4;
-            destination += static_cast<unsigned>(rows * (TW + 1) + words) * 4U;
+#pragma unroll
+            for (int j = 0; j < TileWalk<TW>::period; ++j)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(destination + walk.shared_offset[j]),
+                             "l"(source + walk.global_offset[j])
+                             : "memory");
+            source += TileWalk<TW>::rows * stride;
+            destination += TileWalk<TW>::rows * (TW + 1) * 4U;
         }
         cp_async_commit();
         return;
@@ -110,19 +112,21 @@ __device__ __forceinline__ void tile_store(const uint32_t* tile, uint8_t* pixels
     if (row_mask == 0xFFFFFFFFU && (tile_index + 1) * (TW * 4) <= row_bytes)
     {
         // a whole tile: see tile_load_async
-        TileWalk<TW> walk(lane);
-        uint8_t* destination = pixels + static_cast<size_t>(first_line + walk.r) * stride + tile_index * (TW * 4) + walk.w * 4U;
-        unsigned source = static_cast<unsigned>(__cvta_generic_to_shared(tile + walk.r * (TW + 1) + walk.w));
+        const TileWalk<TW> walk(lane, static_cast<uint32_t>(stride));
+        uint8_t* destination = pixels + static_cast<size_t>(first_line) * stride + tile_index * (TW * 4);
+        unsigned source = static_cast<unsigned>(__cvta_generic_to_shared(tile));
 #pragma unroll
-        for (int k = 0; k < TW; ++k)
+        for (int g = 0; g < TileWalk<TW>::groups; ++g)
         {
-            uint32_t word;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(source) : "memory");
-            *reinterpret_cast<uint32_t*>(destination) = word;
-            int32_t rows, words;
-            walk.step(rows, words);
-            destination += static_cast<size_t>(rows) * stride + words * 4;
-            source += static_cast<unsigned>(rows * (TW + 1) + words) * 4U;
+#pragma unroll
+            for (int j = 0; j < TileWalk<TW>::period; ++j)
+            {
+                uint32_t word;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(source + walk.shared_offset[j]) : "memory");
+                *reinterpret_cast<uint32_t*>(destination + walk.global_offset[j]) = word;
+            }
+            destination += TileWalk<TW>::rows * stride;
+            source += TileWalk<TW>::rows * (TW + 1) * 4U;
         }
         return;
     }

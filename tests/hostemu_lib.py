@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "charls_b200", "csrc")
 class HostEmu:
     def __init__(self):
         src = os.path.join(HOSTEMU_DIR, "hostemu.cpp")
-        deps = [src] + [os.path.join(CSRC, f) for f in ("jls_codec.cuh", "jls_interval.cuh", "jls_common.h", "jls_params.hpp")]
+        deps = [src] + [os.path.join(CSRC, f) for f in ("jls_codec.cuh", "jls_fast.cuh", "jls_interval.cuh", "jls_common.h", "jls_params.hpp")]
         if not os.path.exists(HOSTEMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOSTEMU_LIB) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + CSRC, "-o", HOSTEMU_LIB, src])
         self.dll = C.CDLL(HOSTEMU_LIB)

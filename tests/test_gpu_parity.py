@@ -464,11 +464,15 @@ def encode_scan_by_scan(lib, w, h, bits, component_count, scans, restart_interva
 
 
 def decode_with_scan_getters(lib, stream, component_count):
+    """(pixels, [(near, interleave mode) per component]) or the error code."""
     from charls_b200.codec import JpegLSDecoder
 
     with JpegLSDecoder(lib) as dec:
-        dec.source(stream).read_header()
-        raw = dec.decode()
+        try:
+            dec.source(stream).read_header()
+            raw = dec.decode()
+        except CharlsError as error:
+            return error.errc
         return raw.tobytes(), [(dec.near_lossless(c), dec.interleave_mode(c)) for c in range(component_count)]
 
 
@@ -509,16 +513,25 @@ def test_frames_coded_scan_by_scan(product, oracle):
             assert marked[sc.data_offset : sc.data_end] == oracle.encode_scan(p, np.ascontiguousarray(pixels)), tag + (first,)
             first += count
         want_getters = [(near, ilv) for _, count, ilv, near, _ in scans for _ in range(count)]
+        # The reference writes the preset parameters (LSE) in front of the first scan only
+        # (src/charls_jpegls_encoder.cpp:201-207): a later scan coded with other parameters is decoded with the first
+        # scan's.  That is the reference's behaviour, so it is ours; only the reference can say what comes out.
+        decodable = len({preset for _, _, _, _, preset in scans}) == 1
         decoded = {}
         for ri, stream in ((0, plain), (1, marked)):
-            # near-lossless reconstruction depends on the restart interval: the oracle decodes what it coded the same way
-            expected = b"".join(oracle_reconstruction(oracle, w, h, bits, *scan, ri) for scan in scans)
             decoded[ri] = decode_with_scan_getters(product, stream, cc)
-            assert decoded[ri] == (expected, want_getters), tag + (ri,)
+            if decodable:
+                # near-lossless reconstruction depends on the restart interval: the oracle decodes what it coded
+                expected = b"".join(oracle_reconstruction(oracle, w, h, bits, *scan, ri) for scan in scans)
+                assert decoded[ri] == (expected, want_getters), tag + (ri,)
         if reference is not None:
             assert plain == encode_scan_by_scan(reference, w, h, bits, cc, scans), tag
-            assert decode_with_scan_getters(reference, marked, cc) == decoded[1], tag
-            assert decode_with_scan_getters(reference, plain, cc) == decoded[0], tag
+            for ri, stream in ((0, plain), (1, marked)):
+                theirs = decode_with_scan_getters(reference, stream, cc)
+                if decodable or not isinstance(theirs, int):
+                    assert decoded[ri] == theirs, tag + (ri,)
+                # else: the reference gave up on a scan decoded with the wrong parameters; which error a damaged scan
+                # ends in depends on its read-cache schedule, not asserted
 
 
 def oracle_reconstruction(oracle, w, h, bits, pixels, count, ilv, near, preset, ri):

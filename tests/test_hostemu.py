@@ -72,6 +72,17 @@ def test_presets_masking_and_long_runs(oracle, hostemu):
     check_scan(oracle, hostemu, z, 8, 1, 0, 0, 0, 0)
 
 
+def test_stuffed_bytes_on_wide_noise_lines(oracle, hostemu):
+    """Long incompressible lines: hundreds of 0xFF bytes per line, so both sides of the bit writer's and reader's
+    word paths (plain / stuffed, jls_fast.cuh FastWriter::flush_word, FastReader::refill_once) run back to back."""
+    for bits, cc, ilv in ((8, 1, 0), (12, 1, 0), (16, 1, 0), (16, 3, 2), (8, 3, 2)):
+        img = s_noise(3, 4099, bits, cc, seed=bits + cc, layout="interleaved")
+        sp = oracle.params(4099, 3, bits, cc, 0, ilv, 0, None, 1)
+        assert oracle.encode_scan(sp, img).count(b"\xff") > 20
+        for near in (0, 1):
+            check_scan(oracle, hostemu, img, bits, cc, near, ilv, 0, 1)
+
+
 def test_golden_vectors(oracle, hostemu, golden):
     """Kernel code == reference-made streams (restart interval 1 stitched from per-row reference encodings)."""
     from tests import jlsio
