@@ -25,6 +25,9 @@
 #define JLS_LIKELY(x) (x)
 #endif
 
+#ifndef JLS_READER_DEPTH_NC3
+#define JLS_READER_DEPTH_NC3 2
+#endif
 #ifndef JLS_STUFFED_WORD_PATH
 #define JLS_STUFFED_WORD_PATH 1
 #endif
@@ -447,7 +450,8 @@ JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t r
 // of the warp at the same time, and the refill inside get_golomb()/read() is a rarely taken fall-back.  With a 64-bit
 // window some lane of the warp needed a word at nearly every symbol and the whole warp paid for the refill each time.
 // ---------------------------------------------------------------------------------------------------------------------
-struct FastReader
+template<int DEPTH>
+struct FastReaderT
 {
     uint32_t c3, c2, c1, c0; // the window, left aligned: c3 holds the next bits
     int32_t valid;           // valid bits in the window
@@ -459,8 +463,9 @@ struct FastReader
     const uint32_t* wptr; // aligned word that holds the next byte to fetch
     uint32_t cur;         // *wptr
     uint32_t ahead;       // wptr[1], loaded one refill early so that its latency is hidden behind several pixels of work
-                          // (a second word of look-ahead was tried for top-ups that take two words -- 16-bit RGB -- and
-                          // changed nothing there while costing the one-component decoders 2 %: profiles/r1_notes.md)
+    uint32_t ahead2;      // DEPTH == 2: wptr[2].  A top-up that takes two words (three 16-bit samples per pixel) otherwise
+                          // waits for the load its own first word has just issued; the one-component decoders rarely take
+                          // two words and lose 2 % to the extra move, so they stay at DEPTH 1
     uint32_t shift;       // 8 * (offset of the next byte inside *wptr)
 
     static constexpr int32_t full_mark = 96; // a refill appends words while valid <= full_mark
@@ -483,6 +488,7 @@ struct FastReader
         bad = 0;
         cur = remaining > 0 ? *wptr : 0U;
         ahead = guard > 0 ? wptr[1] : 0U;
+        ahead2 = DEPTH == 2 && guard > 4 ? wptr[2] : 0U;
         refill();
     }
 
@@ -527,7 +533,15 @@ struct FastReader
 #if defined(__CUDA_ARCH__)
         __builtin_assume(__isGlobal(wptr));
 #endif
-        ahead = guard > 0 ? wptr[1] : 0U; // needed only at the next refill
+        if (DEPTH == 2)
+        {
+            ahead = ahead2;
+            ahead2 = guard > 4 ? wptr[2] : 0U; // needed two refills from now
+        }
+        else
+        {
+            ahead = guard > 0 ? wptr[1] : 0U; // needed only at the next refill
+        }
         if (JLS_LIKELY(remaining >= 4 && (prev_ff | has_ff_byte(w)) == 0))
         {
             append(w, 32);
@@ -559,11 +573,51 @@ struct FastReader
             refill_once();
     }
 
+    // DEPTH == 2, valid <= 64: two words in one step.  Both come from registers that were loaded at an earlier top-up, and
+    // the loads issued here go straight into `ahead` and `ahead2`: no instruction reads a register whose load is still
+    // in flight.  (Two refill_once() in a row cannot do that: the second one has to move the word the first one has just
+    // requested, and even a move waits for the load -- ncu, cfg4: a fifth of the decoder's stall samples.)
+    JLS_HD void refill_pair()
+    {
+        const uint32_t w1 = bswap32(funnel_r(cur, ahead, shift));
+        const uint32_t w2 = bswap32(funnel_r(ahead, ahead2, shift));
+        if (JLS_LIKELY(remaining >= 8 && (prev_ff | has_ff_byte(w1) | has_ff_byte(w2)) == 0))
+        {
+            cur = ahead2;
+            wptr += 2;
+            guard -= 8;
+#if defined(__CUDA_ARCH__)
+            __builtin_assume(__isGlobal(wptr));
+#endif
+            ahead = guard > 0 ? wptr[1] : 0U;
+            ahead2 = guard > 4 ? wptr[2] : 0U;
+            // 64 bits at bit `valid` of the window; everything below the valid bits is zero
+            const uint64_t v = (static_cast<uint64_t>(w1) << 32) | w2;
+            const uint64_t upper = valid < 64 ? v >> valid : 0U;
+            const uint64_t lower = valid > 0 ? v << (64 - valid) : 0U;
+            c3 |= static_cast<uint32_t>(upper >> 32);
+            c2 |= static_cast<uint32_t>(upper);
+            c1 |= static_cast<uint32_t>(lower >> 32);
+            c0 |= static_cast<uint32_t>(lower);
+            valid += 64;
+            remaining -= 8;
+        }
+        else
+        {
+            refill_once();
+            refill_once();
+        }
+    }
+
     // the pixel loop's cadence call (all lanes of a warp together)
     JLS_HD void top_up()
     {
         if (valid <= full_mark)
+        {
+            if (DEPTH == 2 && valid <= 64)
+                refill_pair();
             refill();
+        }
     }
 
     JLS_HD uint32_t read(int32_t count) // count in [1, 31]
@@ -655,7 +709,8 @@ struct FastReader
 };
 
 // reference src/scan_decoder_impl.hpp:305-337; -1 when the run passes the end of the line
-JLS_HD int32_t fast_decode_run_length(FastReader& br, int32_t& run_index, int32_t pixel_count)
+template<typename Reader>
+JLS_HD int32_t fast_decode_run_length(Reader& br, int32_t& run_index, int32_t pixel_count)
 {
     int32_t index = 0;
     while (br.read(1) != 0)
@@ -956,7 +1011,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
 template<int NC, bool LOSSLESS, int LUT_MODE = lut_none>
 struct FastLineDecoder : FastLineState<NC, LUT_MODE>
 {
-    FastReader br;
+    FastReaderT<NC == 3 ? JLS_READER_DEPTH_NC3 : 1> br;
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
     // register and one test on the regular-mode path
     int32_t pending;
