@@ -28,9 +28,6 @@
 #ifndef JLS_READER_DEPTH_NC3
 #define JLS_READER_DEPTH_NC3 2
 #endif
-#ifndef JLS_STUFFED_WORD_PATH
-#define JLS_STUFFED_WORD_PATH 1
-#endif
 
 namespace jls {
 
@@ -279,14 +276,7 @@ struct FastWriter
         }
         else
         {
-#if JLS_STUFFED_WORD_PATH
             flush_word_stuffed(w);
-#else
-            do
-            {
-                emit_one_stuffed_byte();
-            } while (nbits >= 32);
-#endif
         }
     }
 

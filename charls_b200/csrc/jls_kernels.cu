@@ -88,42 +88,17 @@ struct TileShape
     static constexpr int stride_words = words + 1;
 };
 
-// Resident blocks per SM the compiler has to make room for (a register cap).  Three-component pixels are coded by three
-// unrolled copies of the sample path; left alone ptxas spends 120-128 registers on them, 13.7 resident warps per SM were
-// too few to cover the latency of the serial chain (ncu, cfg4: issue slots 61 % busy against 81 % for one component).
-// 0 = no cap (not the same as 1: with an explicit 1 ptxas spends registers freely, 80 instead of 64 for the one-component
-// decoder).
-#ifndef JLS_ENC_MIN_BLOCKS_NC3
-#define JLS_ENC_MIN_BLOCKS_NC3 0
-#endif
-#ifndef JLS_DEC_MIN_BLOCKS_NC3
-#define JLS_DEC_MIN_BLOCKS_NC3 0
-#endif
-#ifndef JLS_ENC_MIN_BLOCKS
-#define JLS_ENC_MIN_BLOCKS 0
-#endif
-#ifndef JLS_ENC_TILE_BUFFERS_NC3
-#define JLS_ENC_TILE_BUFFERS_NC3 2
-#endif
-template<int NC, bool ENCODER>
-constexpr int tiled_min_blocks()
-{
-    return NC == 3 ? (ENCODER ? JLS_ENC_MIN_BLOCKS_NC3 : JLS_DEC_MIN_BLOCKS_NC3) : (ENCODER ? JLS_ENC_MIN_BLOCKS : 0);
-}
-
 template<int NC, bool LOSSLESS, typename S>
-__global__ void __launch_bounds__(fast_block_threads, tiled_min_blocks<NC, true>())
+__global__ void __launch_bounds__(fast_block_threads)
     k_encode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
     constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
-    // Two tile buffers: the next tile is in flight while this one is coded.  Three-component tiles are half as large
-    // again; one buffer (the warp waits for every tile, the other warps of the SM cover for it) leaves room for more
-    // resident blocks.
-    constexpr int buffers = NC == 3 ? JLS_ENC_TILE_BUFFERS_NC3 : 2;
+    // Two tile buffers: the next tile is in flight while this one is coded.  (One buffer and a wait per tile leaves room
+    // for more resident blocks -- 31 instead of 21 for three-component pixels -- and measured 3 % slower.)
     __shared__ RegularContext contexts[5 * fast_block_threads];
-    __shared__ uint32_t tiles[warps][buffers][32 * SW];
+    __shared__ uint32_t tiles[warps][2][32 * SW];
     extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
     // the host only picks this kernel when T3 fits; 8-bit containers get an entry for every sample value (no clamp)
@@ -167,16 +142,10 @@ __global__ void __launch_bounds__(fast_block_threads, tiled_min_blocks<NC, true>
     const int32_t transform = h.transform;
     const bool mask_needed = h.bits != static_cast<int32_t>(8 * sizeof(S));
 
-    if (buffers == 2)
-        tile_load_async<TW>(tiles[warp][0], pixels, stride, first_line, last_line, row_bytes, 0, lane);
+    tile_load_async<TW>(tiles[warp][0], pixels, stride, first_line, last_line, row_bytes, 0, lane);
     for (int32_t t = 0; t < tile_count; ++t)
     {
-        if (buffers == 1)
-        {
-            tile_load_async<TW>(tiles[warp][0], pixels, stride, first_line, last_line, row_bytes, t, lane);
-            cp_async_wait<0>();
-        }
-        else if (t + 1 < tile_count)
+        if (t + 1 < tile_count)
         {
             tile_load_async<TW>(tiles[warp][(t + 1) & 1], pixels, stride, first_line, last_line, row_bytes, t + 1, lane);
             cp_async_wait<1>();
@@ -188,7 +157,7 @@ __global__ void __launch_bounds__(fast_block_threads, tiled_min_blocks<NC, true>
         __syncwarp();
         if (active)
         {
-            const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & (buffers - 1)][lane * SW]);
+            const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
             // two loop registers: the sample pointer and a count-down that is loop condition and drain cadence at once
             // (pixels_per_tile is a multiple of 4: groups end where n is one)
             int32_t n = min(pixels_per_tile, width - t * pixels_per_tile);
@@ -228,7 +197,7 @@ __global__ void __launch_bounds__(fast_block_threads, tiled_min_blocks<NC, true>
 }
 
 template<int NC, bool LOSSLESS, typename S>
-__global__ void __launch_bounds__(fast_block_threads, tiled_min_blocks<NC, false>())
+__global__ void __launch_bounds__(fast_block_threads)
     k_decode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
 {
     constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
@@ -819,35 +788,30 @@ cudaError_t launch(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, Ar
 }
 
 // CHARLS_B200_TRACE_OCCUPANCY=1 prints, once per kernel and shared-memory size, the resident blocks per SM the runtime
-// computes for the tile kernels; CHARLS_B200_CARVEOUT=<percent> sets their preferred shared-memory carveout (experiments).
-void tune_and_trace(const void* kernel, int block_threads, size_t dynamic_shared_bytes)
+// computes for the tile kernels.  (A preferred shared-memory carve-out changes nothing: the driver sizes it for the
+// resident blocks already.)
+void trace_occupancy(const void* kernel, int block_threads, size_t dynamic_shared_bytes)
 {
     static const char* const trace = std::getenv("CHARLS_B200_TRACE_OCCUPANCY");
-    static const char* const carveout = std::getenv("CHARLS_B200_CARVEOUT");
-    if (trace == nullptr && carveout == nullptr)
+    if (trace == nullptr)
         return;
     static std::mutex mutex;
     static std::set<std::pair<const void*, size_t>> seen;
     const std::lock_guard<std::mutex> lock(mutex);
     if (!seen.insert({kernel, dynamic_shared_bytes}).second)
         return;
-    if (carveout != nullptr)
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(carveout));
-    if (trace != nullptr)
-    {
-        int blocks = 0;
-        cudaFuncAttributes attributes{};
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, block_threads, dynamic_shared_bytes);
-        cudaFuncGetAttributes(&attributes, kernel);
-        std::fprintf(stderr, "charls_b200: kernel %p: %d registers, %zu + %zu bytes shared, %d resident blocks per SM\n", kernel,
-                     attributes.numRegs, attributes.sharedSizeBytes, dynamic_shared_bytes, blocks);
-    }
+    int blocks = 0;
+    cudaFuncAttributes attributes{};
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, block_threads, dynamic_shared_bytes);
+    cudaFuncGetAttributes(&attributes, kernel);
+    std::fprintf(stderr, "charls_b200: kernel %p: %d registers, %zu + %zu bytes shared, %d resident blocks per SM\n", kernel,
+                 attributes.numRegs, attributes.sharedSizeBytes, dynamic_shared_bytes, blocks);
 }
 
 template<typename Kernel, typename... Args>
 cudaError_t launch_with_shared(Kernel kernel, dim3 grid, dim3 block, size_t dynamic_shared_bytes, cudaStream_t stream, Args... args)
 {
-    tune_and_trace(reinterpret_cast<const void*>(kernel), static_cast<int>(block.x), dynamic_shared_bytes);
+    trace_occupancy(reinterpret_cast<const void*>(kernel), static_cast<int>(block.x), dynamic_shared_bytes);
     kernel<<<grid, block, dynamic_shared_bytes, stream>>>(args...);
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     ++t_kernel_launches;
