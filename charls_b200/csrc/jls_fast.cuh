@@ -25,6 +25,10 @@
 #define JLS_LIKELY(x) (x)
 #endif
 
+// how lossless 16-bit samples are written: write_immediate (0) or write_wide (2), see FastWriter::put
+#ifndef JLS_WRITER_MODE_16
+#define JLS_WRITER_MODE_16 2
+#endif
 #ifndef JLS_READER_DEPTH_NC3
 #define JLS_READER_DEPTH_NC3 2
 #endif
@@ -35,6 +39,7 @@ namespace jls {
 struct HotParams
 {
     int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init, transform;
+    int32_t one; // the value 1, opaque to the compiler on the device (see FastLineState::select_context)
     uint32_t dq_magic;
     uint32_t sign_scale; // 2^(32 - bits)
     // Optional table |Q(-Ra)| for Ra in [0, context_lut_last]; larger Ra use the last entry (they are >= T3).  The tile
@@ -95,6 +100,7 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.range_dq = p.range_dq;
     h.a_init = p.a_init;
     h.transform = p.transform;
+    h.one = 1;
     h.dq_magic = p.dq_magic;
     h.sign_scale = 1U << (32 - p.bits_per_sample);
     h.context_lut = nullptr;
@@ -127,6 +133,7 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
         scratch[10] = static_cast<int32_t>(h.sign_scale);
         scratch[11] = h.context_lut_last;
         scratch[12] = h.transform;
+        scratch[13] = 1;
     }
     __syncwarp();
     h.t1 = scratch[0];
@@ -142,8 +149,9 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
     h.sign_scale = static_cast<uint32_t>(scratch[10]);
     h.context_lut_last = scratch[11];
     h.transform = scratch[12];
+    h.one = scratch[13];
 }
-constexpr int hot_scratch_words = 13;
+constexpr int hot_scratch_words = 14;
 #endif
 
 template<bool LOSSLESS>
@@ -223,10 +231,21 @@ JLS_HD uint8_t context_lut_entry(const CodecParams& p, int32_t ra_value)
 // ---------------------------------------------------------------------------------------------------------------------
 // Bit writer for a slot that is large enough by construction (worst_case_interval_bytes): no capacity checks.
 // ---------------------------------------------------------------------------------------------------------------------
+enum : int
+{
+    write_immediate = 0,
+    write_deferred = 1,
+    write_wide = 2
+};
+
+template<bool LOSSLESS, typename S>
+constexpr int writer_mode = LOSSLESS && sizeof(S) == 2 ? JLS_WRITER_MODE_16 : write_deferred;
+
 struct FastWriter
 {
     uint64_t acc;        // pending bits in the low `nbits` bits
-    int32_t nbits;       // < 32 between calls
+    uint32_t acc_hi;     // write_wide only: bits 64..95 of the accumulator
+    int32_t nbits;       // < 32 between calls (write_immediate), <= 64 (write_deferred), < 96 (write_wide)
     uint32_t pend;       // pending output bytes in the low pend_shift / 8 bytes
     uint32_t pend_shift; // 8 * (number of pending bytes), 0..24
     uint32_t prev_ff;    // last emitted byte was 0xFF
@@ -236,6 +255,7 @@ struct FastWriter
     JLS_HD void init(uint8_t* destination)
     {
         acc = 0;
+        acc_hi = 0;
         nbits = 0;
         pend = 0;
         pend_shift = 0;
@@ -264,10 +284,20 @@ struct FastWriter
         prev_ff = (b == 0xFFU) ? 1U : 0U;
     }
 
+    // The 32 bits on top of the accumulator, nbits >= 32 (WIDE: nbits < 96 and the accumulator is acc_hi : acc).
+    template<bool WIDE>
+    JLS_HD uint32_t top_word() const
+    {
+        if (WIDE && nbits > 64)
+            return static_cast<uint32_t>(acc >> (nbits - 32)) | (acc_hi << (96 - nbits));
+        return static_cast<uint32_t>(acc >> (nbits - 32));
+    }
+
     // Moves one 32-bit word (four stuffed bytes when a 0xFF is around) from the accumulator to the slot; nbits >= 32.
+    template<bool WIDE = false>
     JLS_HD void flush_word()
     {
-        const uint32_t w = static_cast<uint32_t>(acc >> (nbits - 32));
+        const uint32_t w = top_word<WIDE>();
         if (JLS_LIKELY((prev_ff | has_ff_byte(w)) == 0))
         {
             *wp++ = bswap32(funnel_r(w, pend, pend_shift));
@@ -276,13 +306,15 @@ struct FastWriter
         }
         else
         {
-            flush_word_stuffed(w);
+            flush_word_stuffed<WIDE>(w);
         }
     }
 
     // The same word when a 0xFF byte is around: four output bytes again, the byte after a 0xFF takes seven bits, so 28 to
     // 32 bits leave the accumulator.  Straight-line (five instructions per byte): a warp takes this path whenever ONE of
-    // its lanes meets a 0xFF, at a fifth of all drains for 8-bit data.  Ends with nbits < 32 like the plain path.
+    // its lanes meets a 0xFF, at a fifth of all drains for 8-bit data.  Ends with nbits < 32 like the plain path unless
+    // WIDE (whose callers loop).
+    template<bool WIDE>
     JLS_HD void flush_word_stuffed(uint32_t w)
     {
         for (;;)
@@ -304,9 +336,9 @@ struct FastWriter
             *wp++ = bswap32(funnel_r(out, pend, pend_shift));
             pend = out;
             nbits -= 32 - left;
-            if (JLS_LIKELY(nbits < 32))
+            if (WIDE || JLS_LIKELY(nbits < 32))
                 return;
-            w = static_cast<uint32_t>(acc >> (nbits - 32)); // up to four stuffed bits stayed behind
+            w = top_word<false>(); // up to four stuffed bits stayed behind
             if ((prev_ff | has_ff_byte(w)) == 0)
             {
                 *wp++ = bswap32(funnel_r(w, pend, pend_shift));
@@ -321,12 +353,22 @@ struct FastWriter
     // drain() (all lanes of a warp at the same pixel), so the branch below is taken only after unusually long codes.
     // A flush that any one lane needs costs the whole warp its ~15 instructions: at ~4 bits per pixel some lane needed
     // one at almost every pixel (profiles/r1_notes.md), a drain every 4 pixels costs a quarter of that.
-    // DEFERRED = false flushes as soon as 32 bits are pending (best when most samples produce a word anyway: lossless
-    // 16-bit data at 10+ bits per sample); DEFERRED = true leaves it to drain().
-    template<bool DEFERRED>
+    // write_immediate flushes as soon as 32 bits are pending; write_deferred leaves it to drain() (the accumulator holds 64
+    // bits: right for a few bits per sample); write_wide does the same with a 96-bit accumulator (lossless 16-bit data at
+    // 12 bits per sample: three samples of a pixel fit between two drains, where write_immediate has a word ready in
+    // 13 of 32 lanes at every sample and walks the whole warp through the flush each time).
+    template<int MODE>
     JLS_HD void put(uint32_t value, int32_t count)
     {
-        if (DEFERRED)
+        if (MODE == write_wide)
+        {
+            if (JLS_UNLIKELY(nbits + count > 95)) // top_word() needs nbits < 96
+                drain<write_wide>();
+            acc_hi = funnel_l(static_cast<uint32_t>(acc >> 32), acc_hi, static_cast<uint32_t>(count));
+            acc = (acc << count) | value;
+            nbits += count;
+        }
+        else if (MODE == write_deferred)
         {
             if (JLS_UNLIKELY(nbits + count > 64))
             {
@@ -348,14 +390,15 @@ struct FastWriter
     }
 
     // brings nbits below 32
+    template<int MODE = write_deferred>
     JLS_HD void drain()
     {
         while (nbits >= 32)
-            flush_word();
+            flush_word<MODE == write_wide>();
     }
 
     // limited-length Golomb code (T.87 A.5.3; reference src/scan_encoder_core.hpp:69-103)
-    template<bool DEFERRED>
+    template<int MODE>
     JLS_HD void put_golomb(const HotParams& h, int32_t k, int32_t mapped, int32_t escape)
     {
         const int32_t high = mapped >> k;
@@ -363,21 +406,21 @@ struct FastWriter
         if (JLS_LIKELY(high < imin(escape, 32 - k))) // no escape and length <= 32: one compare
         {
             // mapped = high << k | low and the code word is 1 << k | low: flip the bits in which high differs from 1
-            put<DEFERRED>(static_cast<uint32_t>(mapped) ^ (static_cast<uint32_t>(high ^ 1) << k), length);
+            put<MODE>(static_cast<uint32_t>(mapped) ^ (static_cast<uint32_t>(high ^ 1) << k), length);
             return;
         }
         // long code word (more than 32 bits) or escape code: unary part in at most two pieces, then the binary part
         int32_t zeros = high < escape ? high : escape;
         if (zeros > 31)
         {
-            put<DEFERRED>(0, 31);
+            put<MODE>(0, 31);
             zeros -= 31;
         }
-        put<DEFERRED>(1, zeros + 1);
+        put<MODE>(1, zeros + 1);
         if (high < escape)
-            put<DEFERRED>(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
+            put<MODE>(static_cast<uint32_t>(mapped) & ((1U << k) - 1U), k);
         else
-            put<DEFERRED>(static_cast<uint32_t>(mapped - 1) & ((1U << h.qbpp) - 1U), h.qbpp);
+            put<MODE>(static_cast<uint32_t>(mapped - 1) & ((1U << h.qbpp) - 1U), h.qbpp);
     }
 
     // reference src/scan_encoder.hpp:103-115: zero-pad to a byte; a final 0xFF is followed by a zero byte
@@ -411,12 +454,12 @@ struct FastWriter
 };
 
 // reference src/scan_encoder.hpp:53-73
-template<bool DEFERRED>
+template<int MODE>
 JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t run_length, bool end_of_line)
 {
     while (run_length >= (1 << run_order(run_index)))
     {
-        bw.put<DEFERRED>(1, 1);
+        bw.put<MODE>(1, 1);
         run_length -= 1 << run_order(run_index);
         if (run_index < 31)
             ++run_index;
@@ -424,11 +467,11 @@ JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t r
     if (end_of_line)
     {
         if (run_length != 0)
-            bw.put<DEFERRED>(1, 1);
+            bw.put<MODE>(1, 1);
     }
     else
     {
-        bw.put<DEFERRED>(static_cast<uint32_t>(run_length), run_order(run_index) + 1);
+        bw.put<MODE>(static_cast<uint32_t>(run_length), run_order(run_index) + 1);
     }
 }
 
@@ -811,16 +854,25 @@ struct FastLineState
             ra[c] = 0;
     }
 
+    // FORCE_BRANCH (device): in the three-component kernels ptxas turns the short body into predicated instructions all the
+    // same -- seven issue slots per sample that do nothing on smooth data.  A loop of (opaque) one iteration cannot be
+    // predicated.  Measured on cfg4: decoder 4.56 -> 4.49 ms; the encoder does not gain and keeps the plain form.
+    template<bool FORCE_BRANCH = false>
     JLS_HD void select_context(const HotParams& h, int32_t index)
     {
         // a branch, not predication: seven instructions that a warp skips for as long as its lines stay in their contexts
         if (JLS_UNLIKELY(index != cached_index))
         {
-            store_context(cached_index, cached);
-            cached = load_context(index);
-            cached_index = index;
-            if (USE_LUT)
-                load_reciprocal(h);
+#if defined(__CUDA_ARCH__)
+            for (int32_t once = FORCE_BRANCH ? h.one : 1; once > 0; --once)
+#endif
+            {
+                store_context(cached_index, cached);
+                cached = load_context(index);
+                cached_index = index;
+                if (USE_LUT)
+                    load_reciprocal(h);
+            }
         }
     }
 
@@ -887,7 +939,7 @@ struct FastLineState
 // ---------------------------------------------------------------------------------------------------------------------
 // Encoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, bool DEFERRED = true>
+template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, int MODE = write_deferred>
 struct FastLineEncoder : FastLineState<NC, LUT_MODE>
 {
     FastWriter bw;
@@ -919,7 +971,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
         // map(correction ^ e) with correction in {0, -1} equals map(e) ^ (correction & 1): the reference's XOR trick
         // (src/scan_encoder_core.hpp:48-53, src/regular_mode_context.hpp:36-42) costs one conditional bit flip here
         const bool flip = (LOSSLESS ? k : (k | h.near)) == 0 && 2 * c.b + c.n < 1;
-        bw.template put_golomb<DEFERRED>(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
+        bw.template put_golomb<MODE>(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
         this->template update<LOSSLESS>(h, e);
         return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
     }
@@ -931,7 +983,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
         const int32_t k = run_golomb_parameter(c, ri_type);
         const int32_t map = run_compute_map(c, e, k);
         const int32_t e_mapped = 2 * iabs(e) - ri_type - map;
-        bw.template put_golomb<DEFERRED>(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
+        bw.template put_golomb<MODE>(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
         update_run_context(c, e, e_mapped, ri_type, h.reset);
     }
 
@@ -949,7 +1001,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
                 ++run_count; // reconstructed value is Ra (scan_encoder_impl.hpp:258-265)
                 return;
             }
-            fast_encode_run_length<DEFERRED>(bw, this->run_index, run_count, false);
+            fast_encode_run_length<MODE>(bw, this->run_index, run_count, false);
             run_count = 0;
 #pragma unroll
             for (int32_t c = 0; c < NC; ++c)
@@ -980,19 +1032,28 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
     }
 
     // called by the pixel loop every few pixels, by all lanes at the same time (see FastWriter::put)
-    JLS_HD void drain() { bw.drain(); }
+    JLS_HD void drain() { bw.template drain<MODE>(); }
+
+    // pixels between two drain() calls of the pixel loop: write_wide keeps whole pixels of up to ~24 bits per sample
+    // between drains (anything longer drains itself inside put)
+    static constexpr int32_t pixels_per_drain = MODE == write_wide ? (NC == 1 ? 4 : NC == 2 ? 2 : 1) : 4;
 
     // end of a line: a run that reaches the end of the line (reference src/scan_encoder.hpp:62-68)
     JLS_HD void end_line()
     {
         if (run_count != 0)
         {
-            fast_encode_run_length<DEFERRED>(bw, this->run_index, run_count, true);
+            fast_encode_run_length<MODE>(bw, this->run_index, run_count, true);
             run_count = 0;
         }
     }
 
-    JLS_HD uint32_t finish() { return bw.finish(); }
+    JLS_HD uint32_t finish()
+    {
+        if (MODE == write_wide)
+            bw.template drain<write_wide>(); // finish() looks at the lower 64 bits only
+        return bw.finish();
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1030,7 +1091,7 @@ struct FastLineDecoder : FastLineState<NC, LUT_MODE>
     JLS_HD int32_t regular(const HotParams& h, int32_t ra_value)
     {
         const int32_t q = FastLineState<NC, LUT_MODE>::context_index(h, ra_value);
-        this->select_context(h, q);
+        this->template select_context<NC == 3>(h, q);
         RegularContext& c = this->cached;
         const bool negative = NC == 1 || q != 0;
         const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);

@@ -94,7 +94,8 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
     h.context_lut = context_lut;
     h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
     h.reciprocal_lut = reciprocal_lut;
-    FastLineEncoder<NC, LOSSLESS, USE_LUT, !(LOSSLESS && sizeof(S) == 2)> enc;
+    FastLineEncoder<NC, LOSSLESS, USE_LUT, writer_mode<LOSSLESS, S>> enc;
+    constexpr int32_t drain_mask = decltype(enc)::pixels_per_drain - 1;
     uint8_t* slot = job.slots + static_cast<size_t>(interval) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts, context_stride, slot);
@@ -112,7 +113,7 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
             enc.begin_line();
             for (int32_t x = 0; x < width; ++x)
             {
-                if ((x & 3) == 3)
+                if ((x & drain_mask) == drain_mask)
                     enc.drain();
                 const int32_t v[1] = {load_line_component(p, bytes, x, c)};
                 enc.pixel(h, v);
@@ -124,7 +125,7 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
     {
         for (int32_t x = 0; x < width; ++x)
         {
-            if ((x & 3) == 3)
+            if ((x & drain_mask) == drain_mask)
                 enc.drain();
             int32_t v[NC];
             fast_load_pixel<NC, S>(p, h, line, x, v);

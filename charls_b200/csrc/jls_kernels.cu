@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
-    FastLineEncoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, !(LOSSLESS && sizeof(S) == 2)> enc;
+    FastLineEncoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, writer_mode<LOSSLESS, S>> enc;
+    constexpr int32_t drain_mask = decltype(enc)::pixels_per_drain - 1;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
     assume_global(slot);
     enc.begin(h, contexts + threadIdx.x, fast_block_threads, slot);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(fast_block_threads)
             int32_t n = min(pixels_per_tile, width - t * pixels_per_tile);
             do
             {
-                enc.drain(); // every fourth pixel, for all lanes of the warp together
+                enc.drain(); // every fourth pixel (every pixel_per_drain-th), for all lanes of the warp together
 #pragma unroll 1
                 do
                 {
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(fast_block_threads)
                     enc.pixel(h, v);
                     sample += NC;
                     --n;
-                } while ((n & 3) != 0); // the group test is the loop condition: no drain test per pixel
+                } while ((n & drain_mask) != 0); // the group test is the loop condition: no drain test per pixel
             } while (n != 0);
         }
         __syncwarp(); // everybody is done with this buffer before the copy two tiles ahead overwrites it
