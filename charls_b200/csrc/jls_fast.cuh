@@ -856,7 +856,8 @@ struct FastLineState
 
     // FORCE_BRANCH (device): in the three-component kernels ptxas turns the short body into predicated instructions all the
     // same -- seven issue slots per sample that do nothing on smooth data.  A loop of (opaque) one iteration cannot be
-    // predicated.  Measured on cfg4: decoder 4.56 -> 4.49 ms; the encoder does not gain and keeps the plain form.
+    // predicated.  Measured on cfg4: decoder 4.56 -> 4.49 ms; the encoder does not gain and keeps the plain form, and so do
+    // the one-component kernels (predicated there as well; cfg2 decoder 7.49 -> 7.64 ms with the branch, encoder unchanged).
     template<bool FORCE_BRANCH = false>
     JLS_HD void select_context(const HotParams& h, int32_t index)
     {
