@@ -38,3 +38,138 @@ def offset_table(sizes):
         offsets.append(total)
         total += int(s)
     return offsets, total
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One large frame across several GPUs: with one restart interval per line every line is an
+# independent work item, so a frame splits into strips of whole lines.  Rank r codes its strip as an image of its own
+# through the ordinary C ABI; the strips' entropy-coded segments, joined by the restart marker that a single encoder
+# would have written between them, ARE the single-encoder stream (byte for byte), under one header whose frame height is
+# the sum.  Strips start on multiples of eight lines so that the RSTm numbering (m = line mod 8, reference
+# src/scan_decoder.hpp:335-349) continues across the joints.  Only compressed bytes move between ranks.
+# Single-scan frames (one component, or interleaved components) only.
+# ---------------------------------------------------------------------------------------------------------------------
+STRIP_ALIGNMENT = 8
+
+
+def strip_range(height: int, world_size: int, rank: int) -> range:
+    """Lines of the frame owned by `rank`: contiguous, starting on a multiple of eight lines, possibly empty."""
+    groups = (height + STRIP_ALIGNMENT - 1) // STRIP_ALIGNMENT
+    mine = frame_range(groups, world_size, rank)
+    return range(min(mine.start * STRIP_ALIGNMENT, height), min(mine.stop * STRIP_ALIGNMENT, height))
+
+
+def _segments(stream: bytes):
+    """(marker, segment start, payload start) for the marker segments up to and including the first SOS."""
+    if stream[:2] != b"\xff\xd8":
+        raise ValueError("not a JPEG-LS stream")
+    position, out = 2, []
+    while True:
+        if stream[position] != 0xFF:
+            raise ValueError("marker expected")
+        marker = stream[position + 1]
+        length = int.from_bytes(stream[position + 2 : position + 4], "big")
+        out.append((marker, position, position + 2 + length))
+        position += 2 + length
+        if marker == 0xDA:
+            return out
+
+
+def _entropy_segment(stream: bytes):
+    """(header bytes up to the end of the SOS segment, entropy-coded bytes) of a single-scan stream."""
+    segments = _segments(stream)
+    begin = segments[-1][2]
+    if stream[-2:] != b"\xff\xd9":
+        raise ValueError("stream does not end with EOI")
+    return stream[:begin], stream[begin:-2]
+
+
+def _with_height(header: bytes, height: int) -> bytes:
+    """The header with the frame height of its SOF55 segment replaced (heights above 65535 need the LSE form: not here)."""
+    if height > 0xFFFF:
+        raise ValueError("frames taller than 65535 lines are not split")
+    for marker, start, _ in _segments(header + b"\xff\xda\x00\x02"):
+        if marker == 0xF7:
+            return header[: start + 5] + height.to_bytes(2, "big") + header[start + 7 :]
+    raise ValueError("no SOF55 segment")
+
+
+def stitch_strips(strip_streams, strip_heights) -> bytes:
+    """Joins the streams of consecutive strips (each a complete restart-interval-1 stream of its lines) into the stream
+    of the whole frame.  Empty strips (height 0) are skipped."""
+    parts, header, total = [], None, 0
+    for stream, height in zip(strip_streams, strip_heights):
+        if height == 0:
+            continue
+        strip_header, payload = _entropy_segment(stream)
+        if header is None:
+            header = strip_header
+        if total % STRIP_ALIGNMENT != 0:
+            raise ValueError("strips must start on a multiple of eight lines")
+        if parts:
+            parts.append(bytes([0xFF, 0xD0 + (total - 1) % 8]))
+        parts.append(payload)
+        total += height
+    if header is None:
+        raise ValueError("no strips")
+    return _with_height(header, total) + b"".join(parts) + b"\xff\xd9"
+
+
+def split_stream(stream: bytes, world_size: int):
+    """The inverse: cuts a restart-interval-1 stream of a whole frame into one complete stream per rank (None for ranks
+    without lines).  The marker positions come from one vectorised pass over the bytes on the host."""
+    import numpy as np
+
+    header, payload = _entropy_segment(stream)
+    height = None
+    for marker, start, _ in _segments(stream):
+        if marker == 0xF7:
+            height = int.from_bytes(stream[start + 5 : start + 7], "big")
+    data = np.frombuffer(payload, dtype=np.uint8)
+    # inside entropy-coded data 0xFF is followed by a byte below 0x80, so FF D0..D7 is always a restart marker
+    candidates = np.flatnonzero((data[:-1] == 0xFF) & ((data[1:] & 0xF8) == 0xD0))
+    if len(candidates) != height - 1:
+        raise ValueError("not a stream with one restart interval per line")
+    out = []
+    for rank in range(world_size):
+        lines = strip_range(height, world_size, rank)
+        if len(lines) == 0:
+            out.append(None)
+            continue
+        begin = 0 if lines.start == 0 else int(candidates[lines.start - 1]) + 2
+        end = len(payload) if lines.stop == height else int(candidates[lines.stop - 1])
+        out.append(_with_height(header, len(lines)) + payload[begin:end] + b"\xff\xd9")
+    return out
+
+
+def encode_frame_split(image, encode_strip, dist=None):
+    """Every rank passes the whole frame ([H, W] or [H, W, C] numpy array) and `encode_strip(rows) -> bytes`, which codes
+    an array of lines as a restart-interval-1 stream (e.g. functools.partial(charls_b200.codec.encode, ...,
+    restart_interval=1)).  Returns the stream of the whole frame on every rank."""
+    height = image.shape[0]
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lines = strip_range(height, world, rank)
+    mine = encode_strip(image[lines.start : lines.stop]) if len(lines) else b""
+    if world == 1:
+        streams = [mine]
+    else:
+        streams = [None] * world
+        dist.all_gather_object(streams, mine)
+    return stitch_strips(streams, [len(strip_range(height, world, r)) for r in range(world)])
+
+
+def decode_frame_split(stream, decode_strip, dist=None):
+    """Every rank passes the stream of the whole frame and `decode_strip(stream) -> numpy lines`; returns the lines of the
+    whole frame on every rank."""
+    import numpy as np
+
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    mine = split_stream(stream, world)[rank]
+    lines = decode_strip(mine) if mine is not None else None
+    if world == 1:
+        return lines
+    strips = [None] * world
+    dist.all_gather_object(strips, lines)
+    return np.concatenate([s for s in strips if s is not None], axis=0)

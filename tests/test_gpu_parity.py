@@ -542,3 +542,24 @@ def oracle_reconstruction(oracle, w, h, bits, pixels, count, ilv, near, preset, 
     out = np.zeros_like(pixels)
     assert oracle.decode_scan(p, oracle.encode_scan(p, pixels) + b"\xff\xd9", out) > 0
     return out.tobytes()
+
+
+def test_one_frame_coded_in_strips(product, oracle):
+    """charls_b200.sharding: a frame cut into strips of whole lines (what the ranks of a multi-GPU job code), each strip
+    through the ordinary ABI: joined they are the stream of the whole frame, cut again they decode to its lines."""
+    import functools
+
+    from charls_b200 import sharding
+
+    for h, w, bits, cc, ilv, near in ((200, 333, 8, 1, 0, 0), (64, 96, 12, 1, 0, 2), (45, 77, 16, 3, 2, 0)):
+        image = s_mixed(h, w, bits, cc, layout="interleaved") if cc > 1 else s_mixed(h, w, bits)
+        code = functools.partial(encode, product, bits=bits, near_lossless=near, interleave_mode=ilv, restart_interval=1)
+        whole = code(image)
+        assert payloads(whole) == payloads(oracle.encode_image(image, bits, near=near, ilv=ilv, ri=1))
+        expected, _, _ = codec.decode(whole, lib=product)
+        for world in (2, 5):
+            ranges = [sharding.strip_range(h, world, r) for r in range(world)]
+            strips = [code(np.ascontiguousarray(image[r.start : r.stop])) if len(r) else b"" for r in ranges]
+            assert sharding.stitch_strips(strips, [len(r) for r in ranges]) == whole, (h, w, bits, world)
+            lines = [codec.decode(part, lib=product)[0] for part in sharding.split_stream(whole, world) if part is not None]
+            assert np.array_equal(np.concatenate(lines, axis=0), expected), (h, w, bits, world)

@@ -9,6 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from charls_b200 import sharding
 from charls_b200.sharding import frame_range, gather_sizes, offset_table
 
 
@@ -61,3 +62,69 @@ def test_two_ranks_gloo(tmp_path):
     b = np.load(tmp_path / "rank1.npy")
     assert np.array_equal(a, b) and len(a) == 2 * total + 1
     assert a[-1] == a[:total].sum()
+
+
+# -- one frame across several ranks ---------------------------------------------------------------------
+
+STRIP_CASES = ((37, 50, 8, 1, 0, 0), (64, 33, 12, 1, 0, 2), (21, 40, 16, 3, 2, 0), (8, 9, 8, 1, 0, 0), (5, 9, 8, 1, 0, 0))
+
+
+def _strip_image(h, w, bits, cc):
+    from tests.support import s_mixed
+
+    return s_mixed(h, w, bits, cc, layout="interleaved") if cc > 1 else s_mixed(h, w, bits)
+
+
+def test_strip_ranges_cover_the_frame_on_multiples_of_eight():
+    for height in (1, 5, 8, 9, 37, 64, 4096, 65535):
+        for world in (1, 2, 3, 8):
+            ranges = [sharding.strip_range(height, world, r) for r in range(world)]
+            assert [x for r in ranges for x in r] == list(range(height))
+            assert all(r.start % 8 == 0 for r in ranges if len(r))
+
+
+def test_strips_stitch_to_the_single_encoder_stream(oracle, reference):
+    """Strips coded on their own and joined by the restart marker between them are the stream one encoder writes for the
+    whole frame, byte for byte (headers included); the unmodified reference decodes it; cutting it again gives the strips."""
+    from charls_b200 import codec
+
+    for h, w, bits, cc, ilv, near in STRIP_CASES:
+        image = _strip_image(h, w, bits, cc)
+        whole = oracle.encode_image(image, bits, near=near, ilv=ilv, ri=1)
+        expected, _ = oracle.decode_image(whole)
+        for world in (1, 2, 3, 8):
+            ranges = [sharding.strip_range(h, world, r) for r in range(world)]
+            strips = [oracle.encode_image(image[r.start : r.stop], bits, near=near, ilv=ilv, ri=1) if len(r) else b"" for r in ranges]
+            stitched = sharding.stitch_strips(strips, [len(r) for r in ranges])
+            assert stitched == whole, (h, w, bits, world)
+            pixels, _, _ = codec.decode(stitched, lib=reference)
+            assert np.array_equal(pixels, expected)
+            parts = sharding.split_stream(whole, world)
+            assert [p if p is not None else b"" for p in parts] == strips, (h, w, bits, world)
+
+
+def _strip_worker(rank, world, port, result_dir):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests.support import oracle
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    o = oracle()
+    for case, (h, w, bits, cc, ilv, near) in enumerate(STRIP_CASES):
+        image = _strip_image(h, w, bits, cc)
+        stream = sharding.encode_frame_split(image, lambda rows: o.encode_image(rows, bits, near=near, ilv=ilv, ri=1), dist)
+        assert stream == o.encode_image(image, bits, near=near, ilv=ilv, ri=1)
+        pixels = sharding.decode_frame_split(stream, lambda s: o.decode_image(s)[0], dist)
+        assert np.array_equal(pixels, o.decode_image(stream)[0])
+        if rank == 0:
+            with open(os.path.join(result_dir, f"case{case}.jls"), "wb") as f:
+                f.write(stream)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_one_frame_on_two_ranks_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_strip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert len(list(tmp_path.iterdir())) == len(STRIP_CASES)
