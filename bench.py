@@ -467,7 +467,9 @@ def run_gpu_arm(args):
         streams_host = torch.empty((n, codec.stream_capacity), dtype=torch.uint8, pin_memory=True)
         out_host = torch.empty_like(frames_host, pin_memory=True)
         torch.cuda.synchronize()
-        threads = max(1, min(args.e2e_threads, effective_cpus()))
+        # all ranks of a box share its cores: callers mostly wait for the GPU, so twice the cores are handed out, but not more
+        # (waiters that find no core slow everybody down, profiles/r1_notes.md)
+        threads = max(1, min(args.e2e_threads, effective_cpus(), max(4, 2 * effective_cpus() // world)))
         for _ in range(3):
             e2e_round_trip(lib, frames_host, streams_host, out_host, args.workload, threads, not args.e2e_phases)
         passes = max(1, args.e2e_passes)
