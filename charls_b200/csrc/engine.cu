@@ -642,7 +642,8 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     std::memcpy(host_prefixes_.data, header, header_size);
     JLS_CUDA(cudaMemcpyAsync(header_.data, host_prefixes_.data, header_size, cudaMemcpyHostToDevice, stream));
 
-    bool word_aligned = stride % 4 == 0;
+    // the tile kernels keep row offsets of up to three strides in 32 bits (jls_tile.cuh, TileWalk)
+    bool word_aligned = stride % 4 == 0 && stride < (size_t{1} << 30);
     std::vector<ScanJob> jobs(count);
     for (size_t i = 0; i < count; ++i)
     {
@@ -909,7 +910,8 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     const uint64_t launches_before = thread_kernel_launch_count();
 
     size_t max_remaining = 0;
-    bool word_aligned = stride % 4 == 0;
+    // the tile kernels keep row offsets of up to three strides in 32 bits (jls_tile.cuh, TileWalk)
+    bool word_aligned = stride % 4 == 0 && stride < (size_t{1} << 30);
     std::vector<ScanJob> jobs(count);
     for (size_t i = 0; i < count; ++i)
     {
