@@ -5,6 +5,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -128,3 +129,26 @@ def test_one_frame_on_two_ranks_gloo(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_strip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert len(list(tmp_path.iterdir())) == len(STRIP_CASES)
+
+
+def test_strip_helpers_reject_what_they_cannot_join(oracle, reference):
+    from charls_b200 import codec
+
+    image = _strip_image(24, 16, 8, 1)
+    whole = oracle.encode_image(image, 8, ri=1)
+    first = oracle.encode_image(image[:12], 8, ri=1)
+    second = oracle.encode_image(image[12:], 8, ri=1)
+    with pytest.raises(ValueError):
+        sharding.stitch_strips([first, second], [12, 12])  # the second strip does not start on a multiple of eight lines
+    with pytest.raises(ValueError):
+        sharding.split_stream(oracle.encode_image(image, 8, ri=0), 2)  # no restart markers to cut at
+    with pytest.raises(ValueError):
+        sharding.stitch_strips([b"", b""], [0, 0])
+    # fill bytes in front of a restart marker (ISO/IEC 10918-1 B.1.1.2) stay with the strip in front of them
+    header, payload = sharding._entropy_segment(whole)
+    cut = payload.index(b"\xff\xd7")
+    padded = header + payload[:cut] + b"\xff" + payload[cut:] + b"\xff\xd9"
+    parts = sharding.split_stream(padded, 3)
+    pixels = np.concatenate([codec.decode(p, lib=reference)[0] for p in parts if p is not None], axis=0)
+    assert np.array_equal(pixels, image)
+    assert np.array_equal(codec.decode(padded, lib=reference)[0], image)
