@@ -25,10 +25,12 @@
 #define JLS_LIKELY(x) (x)
 #endif
 
+// A/B switches (tools/ab_build.py name:-DJLS_...=value builds a variant of the library; results in profiles/r1_notes.md):
 // how lossless 16-bit samples are written: write_immediate (0) or write_wide (2), see FastWriter::put
 #ifndef JLS_WRITER_MODE_16
 #define JLS_WRITER_MODE_16 2
 #endif
+// stream words the three-component decoder keeps loaded ahead of their use: 1 or 2, see FastReaderT::refill_pair
 #ifndef JLS_READER_DEPTH_NC3
 #define JLS_READER_DEPTH_NC3 2
 #endif
