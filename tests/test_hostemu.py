@@ -141,3 +141,40 @@ def test_golomb_parameter_table_form_is_exact(hostemu):
     check.restype = ctypes.c_uint64
     check.argtypes = [ctypes.c_int32, ctypes.c_int32]
     assert check(64, 1 << 24) == 0
+
+
+def test_damaged_lines_multi_component(oracle, hostemu):
+    """Bit flips and truncation in lines of three-component pixels (the decoder that takes two stream words per top-up,
+    FastReaderT<2>::refill_pair): never a crash; whatever the oracle accepts decodes to the same samples.  Which damaged
+    lines get *rejected* may differ (profiles / DESIGN.md section 8), so that direction is only counted."""
+    rng = np.random.default_rng(11)
+    checked = accepted = 0
+    for bits, cc in ((16, 3), (8, 3), (12, 2), (16, 4)):
+        img = s_mixed(6, 150, bits, cc, seed=bits, layout="interleaved")
+        sp = oracle.params(150, 6, bits, cc, 0, 2, 0, None, 1)
+        good = oracle.encode_scan(sp, img)
+        hp = hostemu.params(sp)
+        for trial in range(40):
+            data = bytearray(good)
+            if trial % 2 == 0:
+                for _ in range(1 + trial % 3):
+                    i = int(rng.integers(0, len(data)))
+                    data[i] ^= 1 << int(rng.integers(0, 8))
+                    if data[i] == 0xFF or (i and data[i - 1] == 0xFF and data[i] >= 0x80):
+                        data[i] = 0x55  # keep the marker structure: this test is about the entropy-coded bits
+            else:
+                cut = int(rng.integers(1, len(data)))
+                # truncation inside a line: keep every restart marker, shorten one interval
+                marker = bytes(data).find(b"\xff", cut)
+                if marker > cut:
+                    del data[cut:marker]
+            data = bytes(data) + b"\xff\xd9"
+            want = np.zeros_like(img)
+            n_oracle = oracle.decode_scan(sp, data, want)
+            got = np.zeros_like(img)
+            n_ours = hostemu.decode(hp, data, got, False)
+            checked += 1
+            if n_oracle >= 0:
+                accepted += 1
+                assert n_ours == n_oracle and np.array_equal(got, want), (bits, cc, trial)
+    assert checked == 160 and accepted > 0
