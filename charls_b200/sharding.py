@@ -47,7 +47,7 @@ def offset_table(sizes):
 # would have written between them, ARE the single-encoder stream (byte for byte), under one header whose frame height is
 # the sum.  Strips start on multiples of eight lines so that the RSTm numbering (m = line mod 8, reference
 # src/scan_decoder.hpp:335-349) continues across the joints.  Only compressed bytes move between ranks.
-# Single-scan frames (one component, or interleaved components) only.
+# Planar frames (one scan per component) are joined scan by scan.
 # ---------------------------------------------------------------------------------------------------------------------
 STRIP_ALIGNMENT = 8
 
@@ -75,13 +75,33 @@ def _segments(stream: bytes):
             return out
 
 
-def _entropy_segment(stream: bytes):
-    """(header bytes up to the end of the SOS segment, entropy-coded bytes) of a single-scan stream."""
+def _scans(stream: bytes):
+    """(bytes in front of the first SOS segment, [(bytes from the end of the previous scan to the end of this scan's SOS
+    segment, entropy-coded bytes of the scan), ...]) of a complete stream."""
+    import numpy as np
+
+    data = np.frombuffer(stream, dtype=np.uint8)
+    # inside entropy-coded data 0xFF is followed by a byte below 0x80; FF D0..D7 are restart markers; anything else ends it
+    ends = np.flatnonzero((data[:-1] == 0xFF) & (data[1:] >= 0x80) & ((data[1:] & 0xF8) != 0xD0) & (data[1:] != 0xFF))
     segments = _segments(stream)
-    begin = segments[-1][2]
-    if stream[-2:] != b"\xff\xd9":
-        raise ValueError("stream does not end with EOI")
-    return stream[:begin], stream[begin:-2]
+    first_sos = segments[-1][1]
+    scans, position = [], first_sos
+    while True:
+        if stream[position : position + 2] != b"\xff\xda":
+            raise ValueError("SOS expected")
+        begin = position + 2 + int.from_bytes(stream[position + 2 : position + 4], "big")
+        following = ends[ends >= begin]
+        if len(following) == 0:
+            raise ValueError("scan without an end")
+        end = int(following[0])
+        while end > begin and stream[end - 1] == 0xFF:  # fill bytes in front of the marker stay outside the scan
+            end -= 1
+        scans.append((stream[position:begin], stream[begin:end]))
+        position = int(following[0])
+        if stream[position + 1] == 0xD9:
+            return stream[:first_sos], scans
+        if stream[position + 1] != 0xDA:
+            raise ValueError("marker segments between scans are not handled")
 
 
 def _with_height(header: bytes, height: int) -> bytes:
@@ -96,61 +116,73 @@ def _with_height(header: bytes, height: int) -> bytes:
 
 def stitch_strips(strip_streams, strip_heights) -> bytes:
     """Joins the streams of consecutive strips (each a complete restart-interval-1 stream of its lines) into the stream
-    of the whole frame.  Empty strips (height 0) are skipped."""
-    parts, header, total = [], None, 0
+    of the whole frame, scan by scan (planar frames have one scan per component).  Empty strips (height 0) are skipped."""
+    header, scan_headers, pieces, total = None, None, None, 0
     for stream, height in zip(strip_streams, strip_heights):
         if height == 0:
             continue
-        strip_header, payload = _entropy_segment(stream)
+        strip_header, scans = _scans(stream)
         if header is None:
-            header = strip_header
+            header, scan_headers, pieces = strip_header, [sos for sos, _ in scans], [[] for _ in scans]
+        if len(scans) != len(pieces):
+            raise ValueError("strips with different numbers of scans")
         if total % STRIP_ALIGNMENT != 0:
             raise ValueError("strips must start on a multiple of eight lines")
-        if parts:
-            parts.append(bytes([0xFF, 0xD0 + (total - 1) % 8]))
-        parts.append(payload)
+        for piece, (_, payload) in zip(pieces, scans):
+            if piece:
+                piece.append(bytes([0xFF, 0xD0 + (total - 1) % 8]))
+            piece.append(payload)
         total += height
     if header is None:
         raise ValueError("no strips")
-    return _with_height(header, total) + b"".join(parts) + b"\xff\xd9"
+    body = b"".join(sos + b"".join(piece) for sos, piece in zip(scan_headers, pieces))
+    return _with_height(header, total) + body + b"\xff\xd9"
 
 
 def split_stream(stream: bytes, world_size: int):
     """The inverse: cuts a restart-interval-1 stream of a whole frame into one complete stream per rank (None for ranks
-    without lines).  The marker positions come from one vectorised pass over the bytes on the host."""
+    without lines).  The marker positions come from vectorised passes over the bytes on the host."""
     import numpy as np
 
-    header, payload = _entropy_segment(stream)
+    header, scans = _scans(stream)
     height = None
     for marker, start, _ in _segments(stream):
         if marker == 0xF7:
             height = int.from_bytes(stream[start + 5 : start + 7], "big")
-    data = np.frombuffer(payload, dtype=np.uint8)
-    # inside entropy-coded data 0xFF is followed by a byte below 0x80, so FF D0..D7 is always a restart marker
-    candidates = np.flatnonzero((data[:-1] == 0xFF) & ((data[1:] & 0xF8) == 0xD0))
-    if len(candidates) != height - 1:
-        raise ValueError("not a stream with one restart interval per line")
+    cuts = []
+    for _, payload in scans:
+        data = np.frombuffer(payload, dtype=np.uint8)
+        candidates = np.flatnonzero((data[:-1] == 0xFF) & ((data[1:] & 0xF8) == 0xD0))
+        if len(candidates) != height - 1:
+            raise ValueError("not a stream with one restart interval per line")
+        cuts.append(candidates)
     out = []
     for rank in range(world_size):
         lines = strip_range(height, world_size, rank)
         if len(lines) == 0:
             out.append(None)
             continue
-        begin = 0 if lines.start == 0 else int(candidates[lines.start - 1]) + 2
-        end = len(payload) if lines.stop == height else int(candidates[lines.stop - 1])
-        out.append(_with_height(header, len(lines)) + payload[begin:end] + b"\xff\xd9")
+        body = b""
+        for (sos, payload), candidates in zip(scans, cuts):
+            begin = 0 if lines.start == 0 else int(candidates[lines.start - 1]) + 2
+            end = len(payload) if lines.stop == height else int(candidates[lines.stop - 1])
+            body += sos + payload[begin:end]
+        out.append(_with_height(header, len(lines)) + body + b"\xff\xd9")
     return out
 
 
-def encode_frame_split(image, encode_strip, dist=None):
-    """Every rank passes the whole frame ([H, W] or [H, W, C] numpy array) and `encode_strip(rows) -> bytes`, which codes
-    an array of lines as a restart-interval-1 stream (e.g. functools.partial(charls_b200.codec.encode, ...,
-    restart_interval=1)).  Returns the stream of the whole frame on every rank."""
-    height = image.shape[0]
+def encode_frame_split(image, encode_strip, dist=None, line_axis=0):
+    """Every rank passes the whole frame (numpy array; lines along `line_axis`: 0 for [H, W] and [H, W, C], 1 for planar
+    [C, H, W]) and `encode_strip(lines) -> bytes`, which codes an array of lines as a restart-interval-1 stream (e.g.
+    functools.partial(charls_b200.codec.encode, ..., restart_interval=1)).  Returns the stream of the whole frame on
+    every rank."""
+    import numpy as np
+
+    height = image.shape[line_axis]
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     lines = strip_range(height, world, rank)
-    mine = encode_strip(image[lines.start : lines.stop]) if len(lines) else b""
+    mine = encode_strip(np.ascontiguousarray(np.take(image, lines, axis=line_axis))) if len(lines) else b""
     if world == 1:
         streams = [mine]
     else:
@@ -159,7 +191,7 @@ def encode_frame_split(image, encode_strip, dist=None):
     return stitch_strips(streams, [len(strip_range(height, world, r)) for r in range(world)])
 
 
-def decode_frame_split(stream, decode_strip, dist=None):
+def decode_frame_split(stream, decode_strip, dist=None, line_axis=0):
     """Every rank passes the stream of the whole frame and `decode_strip(stream) -> numpy lines`; returns the lines of the
     whole frame on every rank."""
     import numpy as np
@@ -172,4 +204,4 @@ def decode_frame_split(stream, decode_strip, dist=None):
         return lines
     strips = [None] * world
     dist.all_gather_object(strips, lines)
-    return np.concatenate([s for s in strips if s is not None], axis=0)
+    return np.concatenate([s for s in strips if s is not None], axis=line_axis)

@@ -67,13 +67,22 @@ def test_two_ranks_gloo(tmp_path):
 
 # -- one frame across several ranks ---------------------------------------------------------------------
 
-STRIP_CASES = ((37, 50, 8, 1, 0, 0), (64, 33, 12, 1, 0, 2), (21, 40, 16, 3, 2, 0), (8, 9, 8, 1, 0, 0), (5, 9, 8, 1, 0, 0))
+STRIP_CASES = ((37, 50, 8, 1, 0, 0), (64, 33, 12, 1, 0, 2), (21, 40, 16, 3, 2, 0), (8, 9, 8, 1, 0, 0), (5, 9, 8, 1, 0, 0),
+               (40, 31, 8, 3, 0, 0), (19, 20, 16, 4, 0, 1))  # the last two: planar frames, one scan per component
 
 
-def _strip_image(h, w, bits, cc):
+def _strip_image(h, w, bits, cc, ilv=2):
     from tests.support import s_mixed
 
-    return s_mixed(h, w, bits, cc, layout="interleaved") if cc > 1 else s_mixed(h, w, bits)
+    return s_mixed(h, w, bits, cc, layout="planar" if ilv == 0 else "interleaved") if cc > 1 else s_mixed(h, w, bits)
+
+
+def _line_axis(cc, ilv):
+    return 1 if cc > 1 and ilv == 0 else 0
+
+
+def _lines(image, lines, axis):
+    return np.ascontiguousarray(np.take(image, lines, axis=axis))
 
 
 def test_strip_ranges_cover_the_frame_on_multiples_of_eight():
@@ -90,12 +99,13 @@ def test_strips_stitch_to_the_single_encoder_stream(oracle, reference):
     from charls_b200 import codec
 
     for h, w, bits, cc, ilv, near in STRIP_CASES:
-        image = _strip_image(h, w, bits, cc)
+        image = _strip_image(h, w, bits, cc, ilv)
+        axis = _line_axis(cc, ilv)
         whole = oracle.encode_image(image, bits, near=near, ilv=ilv, ri=1)
         expected, _ = oracle.decode_image(whole)
         for world in (1, 2, 3, 8):
             ranges = [sharding.strip_range(h, world, r) for r in range(world)]
-            strips = [oracle.encode_image(image[r.start : r.stop], bits, near=near, ilv=ilv, ri=1) if len(r) else b"" for r in ranges]
+            strips = [oracle.encode_image(_lines(image, r, axis), bits, near=near, ilv=ilv, ri=1) if len(r) else b"" for r in ranges]
             stitched = sharding.stitch_strips(strips, [len(r) for r in ranges])
             assert stitched == whole, (h, w, bits, world)
             pixels, _, _ = codec.decode(stitched, lib=reference)
@@ -111,10 +121,11 @@ def _strip_worker(rank, world, port, result_dir):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     o = oracle()
     for case, (h, w, bits, cc, ilv, near) in enumerate(STRIP_CASES):
-        image = _strip_image(h, w, bits, cc)
-        stream = sharding.encode_frame_split(image, lambda rows: o.encode_image(rows, bits, near=near, ilv=ilv, ri=1), dist)
+        image = _strip_image(h, w, bits, cc, ilv)
+        axis = _line_axis(cc, ilv)
+        stream = sharding.encode_frame_split(image, lambda rows: o.encode_image(rows, bits, near=near, ilv=ilv, ri=1), dist, axis)
         assert stream == o.encode_image(image, bits, near=near, ilv=ilv, ri=1)
-        pixels = sharding.decode_frame_split(stream, lambda s: o.decode_image(s)[0], dist)
+        pixels = sharding.decode_frame_split(stream, lambda s: o.decode_image(s)[0], dist, axis)
         assert np.array_equal(pixels, o.decode_image(stream)[0])
         if rank == 0:
             with open(os.path.join(result_dir, f"case{case}.jls"), "wb") as f:
@@ -145,9 +156,9 @@ def test_strip_helpers_reject_what_they_cannot_join(oracle, reference):
     with pytest.raises(ValueError):
         sharding.stitch_strips([b"", b""], [0, 0])
     # fill bytes in front of a restart marker (ISO/IEC 10918-1 B.1.1.2) stay with the strip in front of them
-    header, payload = sharding._entropy_segment(whole)
+    header, [(sos, payload)] = sharding._scans(whole)
     cut = payload.index(b"\xff\xd7")
-    padded = header + payload[:cut] + b"\xff" + payload[cut:] + b"\xff\xd9"
+    padded = header + sos + payload[:cut] + b"\xff" + payload[cut:] + b"\xff\xd9"
     parts = sharding.split_stream(padded, 3)
     pixels = np.concatenate([codec.decode(p, lib=reference)[0] for p in parts if p is not None], axis=0)
     assert np.array_equal(pixels, image)
