@@ -202,7 +202,9 @@ constexpr uint32_t sanity_limit = 1U << 24;
 template<bool LOSSLESS>
 JLS_HD uint32_t fast_update_context(const HotParams& h, RegularContext& c, int32_t e)
 {
-    c.a += iabs(e);
+    // unsigned: on damaged input A keeps growing after the high-water mark has tripped (the line is decoded to its end) and
+    // may pass 2^31; the wrapped value still reads as >= sanity_limit
+    c.a = static_cast<int32_t>(static_cast<uint32_t>(c.a) + static_cast<uint32_t>(iabs(e)));
     c.b += LOSSLESS ? e : e * h.dq;
     const uint32_t water = LOSSLESS ? static_cast<uint32_t>(c.a) : umax(static_cast<uint32_t>(c.a), static_cast<uint32_t>(iabs(c.b)));
     if (JLS_UNLIKELY(c.n == h.reset))
