@@ -209,7 +209,8 @@ static int32_t compute_error_value(const codec* s, int32_t e)
 static int32_t reconstruct(const codec* s, int32_t predicted, int32_t error_value)
 {
     const int32_t d = 2 * s->near_lossless + 1;
-    int32_t v = predicted + error_value * d;
+    /* damaged input can make the product wrap; the reference's int32 arithmetic wraps the same way on the hardware it runs on */
+    int32_t v = (int32_t)((uint32_t)predicted + (uint32_t)error_value * (uint32_t)d);
     if (v < -s->near_lossless)
         v += s->range * d;
     else if (v > s->maxval + s->near_lossless)
@@ -277,7 +278,7 @@ static int32_t run_k(codec* s, const run_ctx* c)
     int32_t k = 0;
     for (; n_test < temp; ++k)
     {
-        n_test <<= 1;
+        n_test = (int32_t)((uint32_t)n_test << 1); /* may wrap on damaged input, like the reference's */
         if (k > 32)
         {
             s->error = JLS_ORACLE_ERR_INVALID_DATA;
