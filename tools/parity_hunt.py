@@ -4,8 +4,10 @@
            (tests/test_abi_differential.py with other seeds)
   kernels  the kernels' codec code compiled for the host vs the oracle, random parameter sets (tests/test_hostemu.py)
   oracle   the oracle vs the unmodified reference, random parameter sets (tests/test_oracle.py)
-usage: python tools/parity_hunt.py abi|kernels|oracle
-End of round 1: abi 388 + 144 seeds, kernels 6080 cases, oracle 1500 cases -- no discrepancy."""
+  damaged  damaged scans (bit flips, truncation, spliced bytes): the kernels' codec code on the host and the oracle, each
+           against the unmodified reference as the arbiter; prints how often each of them accepts / rejects / agrees
+usage: python tools/parity_hunt.py abi|kernels|oracle|damaged
+End of round 1: abi 388 + 144 seeds, kernels 6080 cases, oracle 1500 cases -- no discrepancy; damaged: DESIGN.md section 8."""
 import os
 import sys
 
@@ -134,5 +136,47 @@ def hunt_oracle():
     print("done",n,bad)
 
 
+def hunt_damaged():
+    import numpy as np
+    from charls_b200 import codec
+    from charls_b200.capi import CharlsError
+    from tests.support import oracle, reference_library, s_mixed, s_noise, s_smooth
+    from tests.hostemu_lib import HostEmu
+    from tests import jlsio
+    o=oracle(); he=HostEmu(); ref=reference_library()
+    rng=np.random.default_rng(3)
+    stats={}
+    for bits,cc,ilv,near,ri in ((8,1,0,0,0),(8,1,0,0,1),(12,1,0,2,3),(16,3,2,0,0),(8,3,1,0,2),(16,1,0,0,1),(5,4,2,1,0),(8,3,2,0,1),(2,1,0,0,0)):
+        for gen in (s_mixed,s_smooth,s_noise):
+            img=gen(7,90,bits,cc,seed=bits+cc,layout="interleaved") if cc>1 else gen(7,90,bits,seed=bits)
+            sp=o.params(90,7,bits,cc,near,ilv,0,None,ri); good=o.encode_scan(sp,img); hp=he.params(sp)
+            whole=o.encode_image(img,bits,near=near,ilv=ilv,ri=ri)
+            parsed=jlsio.parse(whole); sc=parsed.scans[0]
+            assert whole[sc.data_offset:sc.data_end]==good
+            for trial in range(60):
+                data=bytearray(good)
+                kind=trial%3
+                if kind==0:
+                    for _ in range(1+trial%4):
+                        i=int(rng.integers(0,len(data))); data[i]^=1<<int(rng.integers(0,8))
+                elif kind==1:
+                    cut=int(rng.integers(1,len(data))); data=data[:cut]
+                else:
+                    i=int(rng.integers(0,len(data))); data[i:i+int(rng.integers(1,6))]=bytes(rng.integers(0,256,size=int(rng.integers(0,5)),dtype=np.uint8))
+                data=bytes(data)
+                stream=whole[:sc.data_offset]+data+b"\xff\xd9"
+                try:
+                    want,_,_=codec.decode(stream,lib=ref); r=0
+                except CharlsError as e:
+                    r=e.errc
+                want_o=np.zeros_like(img); n1=o.decode_scan(sp,data+b"\xff\xd9",want_o)
+                got=np.zeros_like(img); n2=he.decode(hp,data+b"\xff\xd9",got,False)
+                key=("ref ok" if r==0 else "ref err", "oracle ok" if n1>=0 else "oracle err", "ours ok" if n2>=0 else "ours err")
+                same = (r==0 and n2>=0 and np.array_equal(got.reshape(want.shape) if got.size==want.size else got, want))
+                same_o = (r==0 and n1>=0 and np.array_equal(want_o.reshape(want.shape), want))
+                stats[key+(("ours==ref" if same else "ours!=ref") if r==0 and n2>=0 else "", ("oracle==ref" if same_o else "oracle!=ref") if r==0 and n1>=0 else "")]=stats.get(key+(("ours==ref" if same else "ours!=ref") if r==0 and n2>=0 else "", ("oracle==ref" if same_o else "oracle!=ref") if r==0 and n1>=0 else ""),0)+1
+    for k,v in sorted(stats.items(), key=lambda x:-x[1]): print(v,k)
+
+
 if __name__ == "__main__":
-    {"abi": hunt_abi, "kernels": hunt_kernels, "oracle": hunt_oracle}[sys.argv[1]]()
+    {"abi": hunt_abi, "kernels": hunt_kernels, "oracle": hunt_oracle, "damaged": hunt_damaged}[sys.argv[1]]()
