@@ -69,6 +69,7 @@ int32_t set_device(int32_t ordinal) noexcept
     if (ordinal < 0 || ordinal >= count)
         return 101; // invalid_argument
     g_device.store(ordinal);
+    Engine::drop_pooled_except(ordinal);
     return 0;
 }
 
@@ -173,16 +174,35 @@ std::atomic<int> g_borrowed{0};           // engines that codec objects hold rig
 constexpr int blocking_sync_threshold = 6; // see Engine::wait_for
 } // namespace
 
+// The device a new piece of work belongs to: the one set with charlsx_set_device, else the calling thread's current device
+// (-1 when that cannot be asked, e.g. without a driver: the engine then fails in prepare()).
+static int wanted_device() noexcept
+{
+    int wanted = g_device.load();
+    if (wanted < 0 && cudaGetDevice(&wanted) != cudaSuccess)
+    {
+        cudaGetLastError();
+        wanted = -1;
+    }
+    return wanted;
+}
+
+// An engine stays on the device it was first used on (its stream and buffers live there), so the pool hands out only
+// engines of the device the caller is on, or ones that have not been used yet.
 Engine* Engine::acquire()
 {
     g_borrowed.fetch_add(1, std::memory_order_relaxed);
+    const int wanted = wanted_device();
     {
         std::lock_guard<std::mutex> lock(g_pool_mutex);
-        if (!g_pool.empty())
+        for (size_t i = g_pool.size(); i-- > 0;)
         {
-            Engine* engine = g_pool.back();
-            g_pool.pop_back();
-            return engine;
+            Engine* engine = g_pool[i];
+            if (engine->device_ < 0 || engine->device_ == wanted)
+            {
+                g_pool.erase(g_pool.begin() + static_cast<std::ptrdiff_t>(i));
+                return engine;
+            }
         }
     }
     return new Engine;
@@ -195,13 +215,32 @@ void Engine::release(Engine* engine) noexcept
     g_borrowed.fetch_sub(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lock(g_pool_mutex);
-        if (g_pool.size() < pool_limit && (g_device.load() < 0 || engine->device_ < 0 || engine->device_ == g_device.load()))
+        if (g_pool.size() < pool_limit)
         {
             g_pool.push_back(engine);
             return;
         }
     }
     delete engine;
+}
+
+// charlsx_set_device: pooled engines of other devices would never be handed out again
+void Engine::drop_pooled_except(int device) noexcept
+{
+    std::vector<Engine*> stale;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t i = g_pool.size(); i-- > 0;)
+        {
+            if (g_pool[i]->device_ >= 0 && g_pool[i]->device_ != device)
+            {
+                stale.push_back(g_pool[i]);
+                g_pool.erase(g_pool.begin() + static_cast<std::ptrdiff_t>(i));
+            }
+        }
+    }
+    for (Engine* engine : stale)
+        delete engine;
 }
 
 // Waits until `stream` has drained.  A lone caller spins (lowest latency).  When many codec objects are in flight -- one

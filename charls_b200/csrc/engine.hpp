@@ -83,6 +83,7 @@ public:
     // codec object per image (the usual way to use the reference API) do not pay for device allocations every time.
     static Engine* acquire();
     static void release(Engine* engine) noexcept;
+    static void drop_pooled_except(int device) noexcept;
 
 private:
     struct Buffer

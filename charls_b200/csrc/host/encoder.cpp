@@ -85,8 +85,10 @@ struct charls_jpegls_encoder final
         restart_interval_ = interval;
     }
 
-    // reference src/charls_jpegls_encoder.cpp:104-114, plus what restart markers can add: per interval and scan
-    // 2 bytes RSTm + 1 byte padding + 1 stuffed byte after a trailing 0xFF, and the DRI segment.
+    // reference src/charls_jpegls_encoder.cpp:104-114, plus what restart markers can add per interval and component: the
+    // first sample after a restart is predicted from 0 whatever the image looks like and may take a whole LIMIT-bit code
+    // word (a constant 10000 x 1 image costs 6 bytes per line, not a fraction of a bit), then 2 bytes RSTm, 1 byte of
+    // padding and 1 stuffed byte after a trailing 0xFF; and the DRI segment.
     size_t estimated_destination_size() const
     {
         check_operation(frame_info_.width != 0);
@@ -97,7 +99,10 @@ struct charls_jpegls_encoder final
         if (restart_interval_ != 0)
         {
             const size_t intervals = (frame_info_.height + restart_interval_ - 1) / restart_interval_;
-            size = add_saturated(size, checked_mul(intervals * 4U, static_cast<size_t>(frame_info_.component_count)) + 8U);
+            const size_t bits = static_cast<size_t>(frame_info_.bits_per_sample < 2 ? 2 : frame_info_.bits_per_sample);
+            const size_t limit_bits = 2 * (bits + (bits < 8 ? 8 : bits)); // LIMIT of T.87 (reference src/default_traits.hpp:41-45)
+            const size_t per_interval = (limit_bits + 7) / 8 + 4;
+            size = add_saturated(size, checked_mul(checked_mul(intervals, per_interval), static_cast<size_t>(frame_info_.component_count)) + 8U);
         }
         return size;
     }

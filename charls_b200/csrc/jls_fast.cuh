@@ -34,6 +34,22 @@
 #ifndef JLS_READER_DEPTH_NC3
 #define JLS_READER_DEPTH_NC3 2
 #endif
+// round-2 switches (results in profiles/r2_notes.md):
+// 1: the context in use is cached in registers and swapped with shared memory when the index changes (round 1);
+// 0: every sample loads its context from shared memory and stores it back (one LDS.128 + one STS.128 instead of a compare
+//    and seven predicated instructions that issue for every sample whether the context changes or not)
+#ifndef JLS_CONTEXT_CACHE
+#define JLS_CONTEXT_CACHE 0
+#endif
+// 1: the bias step of the context update works on -B with one two-sided clamp (8 instructions instead of 12)
+#ifndef JLS_BIAS_NEGATED
+#define JLS_BIAS_NEGATED 1
+#endif
+// 1: additions of the straight path that ptxas puts on the (busy) integer ALU pipe are written as multiply-adds with an
+//    opaque factor 1 so that they run on the FMA pipe
+#ifndef JLS_FMA_ADDS
+#define JLS_FMA_ADDS 1
+#endif
 
 namespace jls {
 
@@ -41,7 +57,8 @@ namespace jls {
 struct HotParams
 {
     int32_t t1, t2, t3, near, maxval, limit, qbpp, reset, bits, escape, dq, range, range_dq, a_init, transform;
-    int32_t one; // the value 1, opaque to the compiler on the device (see FastLineState::select_context)
+    int32_t one; // the value 1, opaque to the compiler on the device (see FastLineState::select_context, add_fma)
+    int32_t two; // the value 2, likewise (golomb_parameter_reciprocal)
     uint32_t dq_magic;
     uint32_t sign_scale; // 2^(32 - bits)
     // Optional table |Q(-Ra)| for Ra in [0, context_lut_last]; larger Ra use the last entry (they are >= T3).  The tile
@@ -72,13 +89,29 @@ JLS_HD uint32_t reciprocal_lut_entry(int32_t n)
 // t = floor((2a - 1) * reciprocal / 2^32) has that bit length for n <= 64, a < 2^24 (the quotient is overestimated by
 // less than what it takes to reach the next power of two).  a = 0 gives t = -1, whose most significant non-sign bit
 // does not exist: k = 0 like the reference.  Any a gives 0 <= k <= 31.
-JLS_HD int32_t golomb_parameter_reciprocal(int32_t a, uint32_t reciprocal)
+// `two` = 2, as a register the compiler cannot see through on the device: 2a - 1 becomes one IMAD (FMA pipe) instead of an
+// IADD3 on the integer ALU pipe, which is the busy one (JLS_FMA_ADDS)
+JLS_HD int32_t golomb_parameter_reciprocal(int32_t a, uint32_t reciprocal, int32_t two = 2, int32_t one = 1)
 {
 #if defined(__CUDA_ARCH__)
     int32_t position;
-    asm("bfind.s32 %0, %1;" : "=r"(position) : "r"(__mulhi(2 * a - 1, static_cast<int32_t>(reciprocal))));
-    return position + 1; // bfind yields -1 for 0 and for -1
+#if JLS_FMA_ADDS
+    int32_t doubled;
+    asm("mad.lo.s32 %0, %1, %2, -1;" : "=r"(doubled) : "r"(a), "r"(two));
 #else
+    const int32_t doubled = 2 * a - 1;
+#endif
+    asm("bfind.s32 %0, %1;" : "=r"(position) : "r"(__mulhi(doubled, static_cast<int32_t>(reciprocal))));
+#if JLS_FMA_ADDS
+    int32_t k;
+    asm("mad.lo.s32 %0, %1, %2, 1;" : "=r"(k) : "r"(position), "r"(one)); // bfind yields -1 for 0 and for -1
+    return k;
+#else
+    return position + 1;
+#endif
+#else
+    (void)two;
+    (void)one;
     const int64_t t = (static_cast<int64_t>(static_cast<int32_t>(2U * static_cast<uint32_t>(a) - 1U)) * static_cast<int64_t>(reciprocal)) >> 32;
     return t < 0 ? 32 - clz32(static_cast<uint32_t>(~t)) : 32 - clz32(static_cast<uint32_t>(t));
 #endif
@@ -103,6 +136,7 @@ JLS_HD HotParams make_hot_params(const CodecParams& p)
     h.a_init = p.a_init;
     h.transform = p.transform;
     h.one = 1;
+    h.two = 2;
     h.dq_magic = p.dq_magic;
     h.sign_scale = 1U << (32 - p.bits_per_sample);
     h.context_lut = nullptr;
@@ -136,6 +170,7 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
         scratch[11] = h.context_lut_last;
         scratch[12] = h.transform;
         scratch[13] = 1;
+        scratch[14] = 2;
     }
     __syncwarp();
     h.t1 = scratch[0];
@@ -152,17 +187,28 @@ __device__ __forceinline__ void keep_hot_params_in_registers(HotParams& h, volat
     h.context_lut_last = scratch[11];
     h.transform = scratch[12];
     h.one = scratch[13];
+    h.two = scratch[14];
 }
-constexpr int hot_scratch_words = 14;
+constexpr int hot_scratch_words = 15;
 #endif
 
-template<bool LOSSLESS>
+// DEPTH != 0: the sample depth is known at compile time (the tile kernels instantiate 8 and 16 for lossless data that
+// fills its container); 0: it is h.bits.
+template<bool LOSSLESS, int DEPTH = 0>
 JLS_HD int32_t fast_error_value(const HotParams& h, int32_t e)
 {
     if (LOSSLESS)
     {
-        // modulo RANGE = sign extension from bit `bits` (reference src/lossless_traits.hpp:61-65); the left shift is a
-        // multiplication so that it goes to the FMA pipe, the integer ALU pipe is the busy one
+        // modulo RANGE = sign extension from bit `bits` (reference src/lossless_traits.hpp:61-65)
+#if defined(__CUDA_ARCH__)
+        if (DEPTH != 0)
+        {
+            int32_t r;
+            asm("bfe.s32 %0, %1, 0, %2;" : "=r"(r) : "r"(e), "n"(DEPTH)); // one SGXT
+            return r;
+        }
+#endif
+        // the left shift is a multiplication so that it goes to the FMA pipe, the integer ALU pipe is the busy one
         return static_cast<int32_t>(static_cast<uint32_t>(e) * h.sign_scale) >> (32 - h.bits);
     }
     int32_t q = static_cast<int32_t>(mulhi32(static_cast<uint32_t>(iabs(e) + h.near), h.dq_magic));
@@ -177,6 +223,43 @@ JLS_HD int32_t fast_error_value(const HotParams& h, int32_t e)
 JLS_HD int32_t fast_clamp(const HotParams& h, int32_t v) // == correct_prediction: v in [0, maxval] or the nearer bound
 {
     return imin(imax(v, 0), h.maxval);
+}
+
+// max(min(a + b, high), 0) -- one VIADDMNMX.RELU on sm_100a
+JLS_HD int32_t add_clamp_relu(int32_t a, int32_t b, int32_t high)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_s32_relu(a, b, high);
+#else
+    return imax(imin(a + b, high), 0);
+#endif
+}
+
+// a + b on the FMA pipe: an IMAD with the factor h.one, which the compiler cannot see through.  Inline PTX so that NVVM does
+// not reassociate (x * one + 1 and x * one + 2 became one multiply and two additions on the ALU pipe); plain addition on
+// the host.
+JLS_HD int32_t add_fma(const HotParams& h, int32_t a, int32_t b)
+{
+#if defined(__CUDA_ARCH__) && JLS_FMA_ADDS
+    int32_t r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(h.one), "r"(b));
+    return r;
+#else
+    (void)h;
+    return a + b;
+#endif
+}
+
+// unmap_error_value with the sign mask from one SGXT (bit-field extract of bit 0, sign extended)
+JLS_HD int32_t fast_unmap(int32_t m)
+{
+#if defined(__CUDA_ARCH__)
+    int32_t sign;
+    asm("bfe.s32 %0, %1, 0, 1;" : "=r"(sign) : "r"(m));
+    return sign ^ (m >> 1);
+#else
+    return unmap_error_value(m);
+#endif
 }
 
 template<bool LOSSLESS>
@@ -205,6 +288,28 @@ JLS_HD uint32_t fast_update_context(const HotParams& h, RegularContext& c, int32
     // unsigned: on damaged input A keeps growing after the high-water mark has tripped (the line is decoded to its end) and
     // may pass 2^31; the wrapped value still reads as >= sanity_limit
     c.a = static_cast<int32_t>(static_cast<uint32_t>(c.a) + static_cast<uint32_t>(iabs(e)));
+#if JLS_BIAS_NEGATED
+    // The fast path keeps nb = -B in RegularContext::b.  The reference's two branches (B + N <= 0: B += N, at least 1 - N,
+    // C--; B > 0: B -= N, at most 0, C++) are one step d in {-1, 0, +1} and ONE two-sided clamp, because a B that needs no
+    // correction already lies in [1 - N, 0]:  nb' = clamp(nb + d N, 0, N - 1), C' = clamp(C + d, -128, 127) with
+    // d = +1 for nb < 0 (B > 0) and -1 for nb >= N (B + N <= 0).  N - 1 is the count before the increment, and the clamp
+    // is a single VIADDMNMX.RELU.  Halving B (arithmetic shift = floor) is ceil(nb / 2) on the negated value.
+    int32_t nb = c.b - (LOSSLESS ? e : e * h.dq);
+    const uint32_t water = LOSSLESS ? 0U : umax(static_cast<uint32_t>(c.a), static_cast<uint32_t>(iabs(nb)));
+    int32_t n = c.n;
+    if (JLS_UNLIKELY(n == h.reset))
+    {
+        c.a >>= 1;
+        nb = (nb + 1) >> 1;
+        n >>= 1;
+    }
+    const int32_t n1 = add_fma(h, n, 1);
+    const int32_t d = nb < 0 ? 1 : (nb > n ? -1 : 0);
+    c.b = add_clamp_relu(nb, d * n1, n);
+    c.c = imax(imin(c.c + d, 127), -128);
+    c.n = n1;
+    return water;
+#else
     c.b += LOSSLESS ? e : e * h.dq;
     const uint32_t water = LOSSLESS ? static_cast<uint32_t>(c.a) : umax(static_cast<uint32_t>(c.a), static_cast<uint32_t>(iabs(c.b)));
     if (JLS_UNLIKELY(c.n == h.reset))
@@ -224,6 +329,17 @@ JLS_HD uint32_t fast_update_context(const HotParams& h, RegularContext& c, int32
     c.b = low ? b_low : (high ? b_high : c.b);
     c.c = low ? c_low : (high ? c_high : c.c);
     return water;
+#endif
+}
+
+// the reference's error correction applies (before k and NEAR are looked at): 2 B + N < 1 (src/regular_mode_context.hpp:36-42)
+JLS_HD bool fast_correction_sign(const RegularContext& c)
+{
+#if JLS_BIAS_NEGATED
+    return 2 * c.b >= c.n;
+#else
+    return 2 * c.b + c.n < 1;
+#endif
 }
 
 // Fills entry `index` of the context table (callers loop / stride over [0, last]).
@@ -239,11 +355,34 @@ enum : int
 {
     write_immediate = 0,
     write_deferred = 1,
-    write_wide = 2
+    write_wide = 2,
+    // Values from 16 up: "steady" writing with the value as the longest code word of the unchecked path, see
+    // FastWriter::put_golomb.  96-bit accumulator, drained to < 32 bits by all lanes together every
+    // steady_pixels_per_drain pixels; in between, code words of up to MODE bits are appended WITHOUT a capacity test
+    // (31 + NC * pixels * MODE <= 95), anything longer and every run-mode symbol goes through the checked put and ends
+    // with a drain of its own (settle).  Round 1 tested the capacity at every code word: a compare, a branch and a
+    // reconvergence pair per sample on the straight path.
+    write_steady_16 = 16,
+    write_steady_21 = 21,
+    write_steady_32 = 32
 };
 
-template<bool LOSSLESS, typename S>
-constexpr int writer_mode = LOSSLESS && sizeof(S) == 2 ? JLS_WRITER_MODE_16 : write_deferred;
+template<int MODE>
+constexpr bool is_steady = MODE >= 16;
+template<int MODE, int NC>
+constexpr int steady_pixels_per_drain = 64 / (NC * MODE) >= 4 ? 4 : 64 / (NC * MODE) >= 2 ? 2 : 1;
+
+#ifndef JLS_STEADY_WRITER
+#define JLS_STEADY_WRITER 1
+#endif
+// Lossless 16-bit samples need room for ~12-bit code words, everything else (8-bit containers, near-lossless) codes a few
+// bits per sample and drains less often with the short limit.
+template<int NC, bool LOSSLESS, typename S>
+constexpr int writer_mode = !JLS_STEADY_WRITER ? (LOSSLESS && sizeof(S) == 2 ? JLS_WRITER_MODE_16 : write_deferred)
+                            : NC == 3                     ? write_steady_21
+                            : NC == 4                     ? write_steady_16
+                            : LOSSLESS && sizeof(S) == 2 ? write_steady_32
+                                                          : write_steady_16;
 
 struct FastWriter
 {
@@ -364,7 +503,7 @@ struct FastWriter
     template<int MODE>
     JLS_HD void put(uint32_t value, int32_t count)
     {
-        if (MODE == write_wide)
+        if (MODE == write_wide || is_steady<MODE>)
         {
             if (JLS_UNLIKELY(nbits + count > 95)) // top_word() needs nbits < 96
                 drain<write_wide>();
@@ -393,12 +532,28 @@ struct FastWriter
         }
     }
 
+    // steady modes: the same without the capacity test (the caller's contract guarantees nbits + count <= 95)
+    JLS_HD void put_unchecked(uint32_t value, int32_t count)
+    {
+        acc_hi = funnel_l(static_cast<uint32_t>(acc >> 32), acc_hi, static_cast<uint32_t>(count));
+        acc = (acc << count) | value;
+        nbits += count;
+    }
+
     // brings nbits below 32
     template<int MODE = write_deferred>
     JLS_HD void drain()
     {
         while (nbits >= 32)
-            flush_word<MODE == write_wide>();
+            flush_word<MODE == write_wide || is_steady<MODE>>();
+    }
+
+    // steady modes: called after symbols that went through the checked put, restores nbits < 32 for the unchecked ones
+    template<int MODE>
+    JLS_HD void settle()
+    {
+        if (is_steady<MODE>)
+            drain<MODE>();
     }
 
     // limited-length Golomb code (T.87 A.5.3; reference src/scan_encoder_core.hpp:69-103)
@@ -406,6 +561,23 @@ struct FastWriter
     JLS_HD void put_golomb(const HotParams& h, int32_t k, int32_t mapped, int32_t escape)
     {
         const int32_t high = mapped >> k;
+        if (is_steady<MODE>)
+        {
+            // The short code word is built unconditionally and appended behind the rare branch, which zeroes it after
+            // writing the long form: the straight path has no jump over the long form's code.
+            // mapped = high << k | low and the code word is 1 << k | low: flip the bits in which high differs from 1
+            uint32_t value = static_cast<uint32_t>(mapped) ^ (static_cast<uint32_t>(high ^ 1) << k);
+            int32_t length = add_fma(h, high, add_fma(h, k, 1));
+            if (JLS_UNLIKELY(high >= imin(escape, MODE - k))) // an escape, or longer than MODE bits
+            {
+                put_golomb<write_wide>(h, k, mapped, escape);
+                drain<MODE>();
+                value = 0;
+                length = 0;
+            }
+            put_unchecked(value, length);
+            return;
+        }
         const int32_t length = high + 1 + k;
         if (JLS_LIKELY(high < imin(escape, 32 - k))) // no escape and length <= 32: one compare
         {
@@ -782,7 +954,7 @@ enum : int
     lut_full = 2
 };
 
-template<int NC, int LUT_MODE>
+template<int NC, int LUT_MODE, int DEPTH = 0>
 struct FastLineState
 {
     static constexpr bool USE_LUT = LUT_MODE != lut_none;
@@ -865,6 +1037,14 @@ struct FastLineState
     template<bool FORCE_BRANCH = false>
     JLS_HD void select_context(const HotParams& h, int32_t index)
     {
+#if !JLS_CONTEXT_CACHE
+        // no caching: the context travels shared memory -> registers -> shared memory for every sample (update() stores it)
+        (void)FORCE_BRANCH;
+        cached_index = index;
+        cached = load_context(index);
+        if (USE_LUT)
+            load_reciprocal(h);
+#else
         // a branch, not predication: seven instructions that a warp skips for as long as its lines stay in their contexts
         if (JLS_UNLIKELY(index != cached_index))
         {
@@ -879,6 +1059,7 @@ struct FastLineState
                     load_reciprocal(h);
             }
         }
+#endif
     }
 
     // after cached.n changed
@@ -891,9 +1072,9 @@ struct FastLineState
 #endif
     }
 
-    JLS_HD int32_t golomb_k() const
+    JLS_HD int32_t golomb_k(const HotParams& h) const
     {
-        return USE_LUT ? golomb_parameter_reciprocal(cached.a, cached_reciprocal) : golomb_parameter(cached.a, cached.n);
+        return USE_LUT ? golomb_parameter_reciprocal(cached.a, cached_reciprocal, h.two, h.one) : golomb_parameter(cached.a, cached.n);
     }
 
     // context update of the cached context; returns the high-water mark of fast_update_context
@@ -901,8 +1082,12 @@ struct FastLineState
     JLS_HD uint32_t update(const HotParams& h, int32_t e)
     {
         const uint32_t water = fast_update_context<LOSSLESS>(h, cached, e);
+#if !JLS_CONTEXT_CACHE
+        store_context(cached_index, cached);
+#else
         if (USE_LUT)
             load_reciprocal(h);
+#endif
         return water;
     }
 
@@ -944,11 +1129,13 @@ struct FastLineState
 // ---------------------------------------------------------------------------------------------------------------------
 // Encoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, int MODE = write_deferred>
-struct FastLineEncoder : FastLineState<NC, LUT_MODE>
+template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, int MODE = write_deferred, int DEPTH = 0>
+struct FastLineEncoder : FastLineState<NC, LUT_MODE, DEPTH>
 {
     FastWriter bw;
     int32_t run_count;
+    // run-mode symbols take the checked put of the steady modes (see write_steady_16)
+    static constexpr int RUN_WRITE = is_steady<MODE> ? write_wide : MODE;
 
     JLS_HD void begin(const HotParams& h, RegularContext* ctx, int32_t stride, uint8_t* slot)
     {
@@ -959,23 +1146,23 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
 
     JLS_HD void begin_line()
     {
-        FastLineState<NC, LUT_MODE>::begin_line();
+        FastLineState<NC, LUT_MODE, DEPTH>::begin_line();
         run_count = 0;
     }
 
     // regular mode for one sample (reference src/scan_encoder_core.hpp:40-55); prediction = Ra, sign < 0 unless q == 0
     JLS_HD int32_t regular(const HotParams& h, int32_t x, int32_t ra_value)
     {
-        const int32_t q = FastLineState<NC, LUT_MODE>::context_index(h, ra_value);
+        const int32_t q = FastLineState<NC, LUT_MODE, DEPTH>::context_index(h, ra_value);
         this->select_context(h, q);
         RegularContext& c = this->cached;
-        const int32_t k = this->golomb_k();
+        const int32_t k = this->golomb_k(h);
         const bool negative = NC == 1 || q != 0; // a scalar line reaches regular mode only with q != 0
-        const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
-        const int32_t e = fast_error_value<LOSSLESS>(h, negative ? pv - x : x - pv);
+        const int32_t pv = add_clamp_relu(ra_value, negative ? -c.c : c.c, h.maxval); // == correct_prediction(Ra -+ C)
+        const int32_t e = fast_error_value<LOSSLESS, DEPTH>(h, negative ? pv - x : x - pv);
         // map(correction ^ e) with correction in {0, -1} equals map(e) ^ (correction & 1): the reference's XOR trick
         // (src/scan_encoder_core.hpp:48-53, src/regular_mode_context.hpp:36-42) costs one conditional bit flip here
-        const bool flip = (LOSSLESS ? k : (k | h.near)) == 0 && 2 * c.b + c.n < 1;
+        const bool flip = (LOSSLESS ? k : (k | h.near)) == 0 && fast_correction_sign(c);
         bw.template put_golomb<MODE>(h, k, map_error_value(e) ^ (flip ? 1 : 0), h.escape);
         this->template update<LOSSLESS>(h, e);
         return LOSSLESS ? x : fast_reconstruct<false>(h, pv, negative ? -e : e);
@@ -988,7 +1175,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
         const int32_t k = run_golomb_parameter(c, ri_type);
         const int32_t map = run_compute_map(c, e, k);
         const int32_t e_mapped = 2 * iabs(e) - ri_type - map;
-        bw.template put_golomb<MODE>(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
+        bw.template put_golomb<RUN_WRITE>(h, k, e_mapped, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
         update_run_context(c, e, e_mapped, ri_type, h.reset);
     }
 
@@ -1006,7 +1193,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
                 ++run_count; // reconstructed value is Ra (scan_encoder_impl.hpp:258-265)
                 return;
             }
-            fast_encode_run_length<MODE>(bw, this->run_index, run_count, false);
+            fast_encode_run_length<RUN_WRITE>(bw, this->run_index, run_count, false);
             run_count = 0;
 #pragma unroll
             for (int32_t c = 0; c < NC; ++c)
@@ -1014,7 +1201,7 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
                 if (NC == 1)
                 {
                     // Rb = 0 and Ra <= NEAR: |Ra - Rb| <= NEAR always -> RItype 1 (scan_encoder_core.hpp:118-125)
-                    const int32_t e = fast_error_value<LOSSLESS>(h, x[c] - this->ra[c]);
+                    const int32_t e = fast_error_value<LOSSLESS, DEPTH>(h, x[c] - this->ra[c]);
                     interruption_error(h, 1, e);
                     this->ra[c] = LOSSLESS ? x[c] : fast_reconstruct<false>(h, this->ra[c], e);
                 }
@@ -1022,13 +1209,14 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
                 {
                     // per component, RItype 0, prediction Rb = 0 (scan_encoder_core.hpp:133-138)
                     const int32_t s = sign_of(-this->ra[c]);
-                    const int32_t e = fast_error_value<LOSSLESS>(h, s * x[c]);
+                    const int32_t e = fast_error_value<LOSSLESS, DEPTH>(h, s * x[c]);
                     interruption_error(h, 0, e);
                     this->ra[c] = LOSSLESS ? x[c] : fast_reconstruct<false>(h, 0, e * s);
                 }
             }
             if (this->run_index > 0)
                 --this->run_index;
+            bw.template settle<MODE>();
             return;
         }
 #pragma unroll
@@ -1041,21 +1229,22 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
 
     // pixels between two drain() calls of the pixel loop: write_wide keeps whole pixels of up to ~24 bits per sample
     // between drains (anything longer drains itself inside put)
-    static constexpr int32_t pixels_per_drain = MODE == write_wide ? (NC == 1 ? 4 : NC == 2 ? 2 : 1) : 4;
+    static constexpr int32_t pixels_per_drain =
+        is_steady<MODE> ? steady_pixels_per_drain<MODE, NC> : MODE == write_wide ? (NC == 1 ? 4 : NC == 2 ? 2 : 1) : 4;
 
     // end of a line: a run that reaches the end of the line (reference src/scan_encoder.hpp:62-68)
     JLS_HD void end_line()
     {
         if (run_count != 0)
         {
-            fast_encode_run_length<MODE>(bw, this->run_index, run_count, true);
+            fast_encode_run_length<RUN_WRITE>(bw, this->run_index, run_count, true);
             run_count = 0;
         }
     }
 
     JLS_HD uint32_t finish()
     {
-        if (MODE == write_wide)
+        if (MODE == write_wide || is_steady<MODE>)
             bw.template drain<write_wide>(); // finish() looks at the lower 64 bits only
         return bw.finish();
     }
@@ -1064,8 +1253,8 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE>
 // ---------------------------------------------------------------------------------------------------------------------
 // Decoder
 // ---------------------------------------------------------------------------------------------------------------------
-template<int NC, bool LOSSLESS, int LUT_MODE = lut_none>
-struct FastLineDecoder : FastLineState<NC, LUT_MODE>
+template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, int DEPTH = 0>
+struct FastLineDecoder : FastLineState<NC, LUT_MODE, DEPTH>
 {
     FastReaderT<NC == 3 ? JLS_READER_DEPTH_NC3 : 1> br;
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
@@ -1088,22 +1277,22 @@ struct FastLineDecoder : FastLineState<NC, LUT_MODE>
 
     JLS_HD void begin_line()
     {
-        FastLineState<NC, LUT_MODE>::begin_line();
+        FastLineState<NC, LUT_MODE, DEPTH>::begin_line();
         pending = 0;
     }
 
     // reference src/scan_decoder_core.hpp:38-69
     JLS_HD int32_t regular(const HotParams& h, int32_t ra_value)
     {
-        const int32_t q = FastLineState<NC, LUT_MODE>::context_index(h, ra_value);
+        const int32_t q = FastLineState<NC, LUT_MODE, DEPTH>::context_index(h, ra_value);
         this->template select_context<NC == 3>(h, q);
         RegularContext& c = this->cached;
         const bool negative = NC == 1 || q != 0;
-        const int32_t pv = fast_clamp(h, negative ? ra_value - c.c : ra_value + c.c);
-        const int32_t k = this->golomb_k();
-        const bool flip = k == 0 && (LOSSLESS || h.near == 0) && 2 * c.b + c.n < 1; // see the encoder
+        const int32_t pv = add_clamp_relu(ra_value, negative ? -c.c : c.c, h.maxval); // == correct_prediction(Ra -+ C)
+        const int32_t k = this->golomb_k(h);
+        const bool flip = k == 0 && (LOSSLESS || h.near == 0) && fast_correction_sign(c); // see the encoder
         // unmap(m ^ 1) == ~unmap(m): the correction becomes one predicated complement behind the unmapping
-        int32_t e = unmap_error_value(br.get_golomb_steady(h, k, h.escape));
+        int32_t e = fast_unmap(br.get_golomb_steady(h, k, h.escape));
         if (flip)
             e = ~e;
         // The reference's sanity checks -- k >= 16 (src/regular_mode_context.hpp:107-108), |e| > 65535
@@ -1112,7 +1301,11 @@ struct FastLineDecoder : FastLineState<NC, LUT_MODE>
         // path (24 or `escape` zeros at most, shifted by k <= 15, or k >= 16 which trips the limit by itself), so the
         // products cannot wrap.
         const uint32_t marks = umax(static_cast<uint32_t>(k) << 20, static_cast<uint32_t>(iabs(e)) << 8);
-        high_water = umax(umax(high_water, marks), this->template update<LOSSLESS>(h, e));
+        // Lossless: the context's own check (A >= 2^24 after the update) never fires first.  |e| <= 65535 puts the A before
+        // the update above 2^24 - 2^16, and N <= RESET <= 255 then gives k >= 16 for this very symbol (255 << 15 < 2^24 -
+        // 2^16): the k mark has tripped already.  |B| stays below RESET + 65536.  Near-lossless keeps the mark for B.
+        const uint32_t water = this->template update<LOSSLESS>(h, e);
+        high_water = LOSSLESS ? umax(high_water, marks) : umax(umax(high_water, marks), water);
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }
 

@@ -94,7 +94,7 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
     h.context_lut = context_lut;
     h.context_lut_last = imin(p.t3, context_lut_capacity - 1);
     h.reciprocal_lut = reciprocal_lut;
-    FastLineEncoder<NC, LOSSLESS, USE_LUT, writer_mode<LOSSLESS, S>> enc;
+    FastLineEncoder<NC, LOSSLESS, USE_LUT, writer_mode<NC, LOSSLESS, S>> enc;
     constexpr int32_t drain_mask = decltype(enc)::pixels_per_drain - 1;
     uint8_t* slot = job.slots + static_cast<size_t>(interval) * slot_bytes;
     assume_global(slot);

@@ -81,6 +81,27 @@ __global__ void __launch_bounds__(fast_block_threads)
 // Fast path with shared-memory tiles (jls_tile.cuh): the same per-line codec, but the samples travel between HBM and the
 // lanes as coalesced [32 lines x 64/96 bytes] tiles instead of per-lane byte accesses.  Needs 4-byte aligned rows.
 // ---------------------------------------------------------------------------------------------------------------------
+// sample `index` (an immediate) at shared-window address `address`
+template<typename S>
+__device__ __forceinline__ int32_t load_shared_sample(uint32_t address, int32_t index)
+{
+    uint32_t v;
+    if (sizeof(S) == 1)
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(address + static_cast<uint32_t>(index)) : "memory");
+    else
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(address + 2U * static_cast<uint32_t>(index)) : "memory");
+    return static_cast<int32_t>(v);
+}
+
+template<typename S>
+__device__ __forceinline__ void store_shared_sample(uint32_t address, int32_t index, int32_t value)
+{
+    if (sizeof(S) == 1)
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(address + static_cast<uint32_t>(index)), "r"(value) : "memory");
+    else
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(address + 2U * static_cast<uint32_t>(index)), "r"(value) : "memory");
+}
+
 template<int NC>
 struct TileShape
 {
@@ -88,7 +109,9 @@ struct TileShape
     static constexpr int stride_words = words + 1;
 };
 
-template<int NC, bool LOSSLESS, typename S>
+// DEPTH = bits per sample when lossless data fills its container (8 in uint8_t, 16 in uint16_t): depth, MAXVAL and the
+// sign extension of the error value become immediates and no sample needs masking; 0 = any depth (h.bits).
+template<int NC, bool LOSSLESS, typename S, int DEPTH>
 __global__ void __launch_bounds__(fast_block_threads)
     k_encode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
@@ -126,8 +149,13 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.reciprocal_lut = reciprocal_lut;
     h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
+    if (DEPTH != 0)
+    {
+        h.bits = DEPTH;
+        h.maxval = (1 << DEPTH) - 1;
+    }
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
-    FastLineEncoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, writer_mode<LOSSLESS, S>> enc;
+    FastLineEncoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, writer_mode<NC, LOSSLESS, S>, DEPTH> enc;
     constexpr int32_t drain_mask = decltype(enc)::pixels_per_drain - 1;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
     assume_global(slot);
@@ -141,7 +169,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     const int32_t tile_count = (row_bytes + TW * 4 - 1) / (TW * 4);
     const uint32_t last_line = p.interval_count - 1;
     const int32_t transform = h.transform;
-    const bool mask_needed = h.bits != static_cast<int32_t>(8 * sizeof(S));
+    const bool mask_needed = DEPTH == 0 && h.bits != static_cast<int32_t>(8 * sizeof(S));
 
     tile_load_async<TW>(tiles[warp][0], pixels, stride, first_line, last_line, row_bytes, 0, lane);
     for (int32_t t = 0; t < tile_count; ++t)
@@ -158,9 +186,9 @@ __global__ void __launch_bounds__(fast_block_threads)
         __syncwarp();
         if (active)
         {
-            const S* sample = reinterpret_cast<const S*>(&tiles[warp][t & 1][lane * SW]);
-            // two loop registers: the sample pointer and a count-down that is loop condition and drain cadence at once
-            // (pixels_per_tile is a multiple of 4: groups end where n is one)
+            // two loop registers: the sample's shared-memory address and a count-down that is loop condition and drain
+            // cadence at once (pixels_per_tile is a multiple of 4: groups end where n is one); both advance on the FMA pipe
+            uint32_t sample = static_cast<uint32_t>(__cvta_generic_to_shared(&tiles[warp][t & 1][lane * SW]));
             int32_t n = min(pixels_per_tile, width - t * pixels_per_tile);
             do
             {
@@ -171,7 +199,7 @@ __global__ void __launch_bounds__(fast_block_threads)
                     int32_t v[NC];
 #pragma unroll
                     for (int32_t c = 0; c < NC; ++c)
-                        v[c] = sample[c];
+                        v[c] = load_shared_sample<S>(sample, c);
                     if (NC == 3 && transform != 0)
                     {
                         color_forward(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
@@ -183,8 +211,8 @@ __global__ void __launch_bounds__(fast_block_threads)
                             v[c] &= h.maxval;
                     }
                     enc.pixel(h, v);
-                    sample += NC;
-                    --n;
+                    sample = static_cast<uint32_t>(add_fma(h, static_cast<int32_t>(sample), NC * static_cast<int32_t>(sizeof(S))));
+                    n = add_fma(h, n, -1);
                 } while ((n & drain_mask) != 0); // the group test is the loop condition: no drain test per pixel
             } while (n != 0);
         }
@@ -197,7 +225,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     }
 }
 
-template<int NC, bool LOSSLESS, typename S>
+template<int NC, bool LOSSLESS, typename S, int DEPTH>
 __global__ void __launch_bounds__(fast_block_threads)
     k_decode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
 {
@@ -249,7 +277,12 @@ __global__ void __launch_bounds__(fast_block_threads)
     h.reciprocal_lut = reciprocal_lut;
     h.reciprocal_lut_shared = static_cast<uint32_t>(__cvta_generic_to_shared(reciprocal_lut));
     keep_hot_params_in_registers(h, hot_scratch[warp]);
-    FastLineDecoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped> dec;
+    if (DEPTH != 0)
+    {
+        h.bits = DEPTH;
+        h.maxval = (1 << DEPTH) - 1;
+    }
+    FastLineDecoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, DEPTH> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
     dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
@@ -267,7 +300,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     {
         if (coding)
         {
-            S* sample = reinterpret_cast<S*>(&tile[lane * SW]);
+            uint32_t sample = static_cast<uint32_t>(__cvta_generic_to_shared(&tile[lane * SW]));
             const int32_t x0 = t * pixels_per_tile;
             // two loop registers: the sample pointer and a count-down that is loop condition and refill cadence at once;
             // the pixels left in the line are needed on the rare run-mode path only
@@ -288,9 +321,9 @@ __global__ void __launch_bounds__(fast_block_threads)
                         color_inverse(transform, sizeof(S) == 2 ? 0xFFFF : 0xFF, v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
 #pragma unroll
                     for (int32_t c = 0; c < NC; ++c)
-                        sample[c] = static_cast<S>(v[c]);
-                    sample += NC;
-                    --n;
+                        store_shared_sample<S>(sample, c, v[c]);
+                    sample = static_cast<uint32_t>(add_fma(h, static_cast<int32_t>(sample), NC * static_cast<int32_t>(sizeof(S))));
+                    n = add_fma(h, n, -1);
                 } while ((n & (refill_cadence - 1)) != 0); // the group test is the loop condition: no top-up test per pixel
             } while (n != 0);
         }
@@ -845,7 +878,15 @@ cudaError_t launch_encode_fast(const CodecParams& p, bool tiled, dim3 grid, dim3
                                const ScanJob* jobs, size_t slot_bytes)
 {
     if (tiled)
-        return launch_with_shared(k_encode_tiled<NC, LL, S>, grid, block, tiled_dynamic_shared_bytes(p), stream, p, jobs, slot_bytes);
+    {
+        if constexpr (LL)
+        {
+            if (p.bits_per_sample == static_cast<int32_t>(8 * sizeof(S)))
+                return launch_with_shared(k_encode_tiled<NC, LL, S, 8 * sizeof(S)>, grid, block, tiled_dynamic_shared_bytes(p), stream,
+                                          p, jobs, slot_bytes);
+        }
+        return launch_with_shared(k_encode_tiled<NC, LL, S, 0>, grid, block, tiled_dynamic_shared_bytes(p), stream, p, jobs, slot_bytes);
+    }
     if constexpr (NC == 1)
     {
         if (p.interleave == ilv_line)
@@ -858,7 +899,15 @@ template<int NC, bool LL, typename S>
 cudaError_t launch_decode_fast(const CodecParams& p, bool tiled, dim3 grid, dim3 block, cudaStream_t stream, const ScanJob* jobs)
 {
     if (tiled)
-        return launch_with_shared(k_decode_tiled<NC, LL, S>, grid, block, tiled_dynamic_shared_bytes(p), stream, p, jobs);
+    {
+        if constexpr (LL)
+        {
+            if (p.bits_per_sample == static_cast<int32_t>(8 * sizeof(S)))
+                return launch_with_shared(k_decode_tiled<NC, LL, S, 8 * sizeof(S)>, grid, block, tiled_dynamic_shared_bytes(p), stream,
+                                          p, jobs);
+        }
+        return launch_with_shared(k_decode_tiled<NC, LL, S, 0>, grid, block, tiled_dynamic_shared_bytes(p), stream, p, jobs);
+    }
     if constexpr (NC == 1)
     {
         if (p.interleave == ilv_line)
@@ -896,12 +945,14 @@ cudaError_t dispatch_encode_fast(const CodecParams& p, bool rows_word_aligned, d
     const bool tiled = rows_tileable(p, rows_word_aligned);
     switch (p.interleave == ilv_sample ? p.components : 1)
     {
-    case 2:
-        return dispatch_encode_nc<2>(p, tiled, grid, block, stream, jobs, slot_bytes);
     case 3:
         return dispatch_encode_nc<3>(p, tiled, grid, block, stream, jobs, slot_bytes);
+#if !defined(JLS_DEV_SUBSET) // development builds (tools/dev_sass.sh) instantiate the one- and three-component kernels only
+    case 2:
+        return dispatch_encode_nc<2>(p, tiled, grid, block, stream, jobs, slot_bytes);
     case 4:
         return dispatch_encode_nc<4>(p, tiled, grid, block, stream, jobs, slot_bytes);
+#endif
     default:
         return dispatch_encode_nc<1>(p, tiled, grid, block, stream, jobs, slot_bytes);
     }
@@ -913,12 +964,14 @@ cudaError_t dispatch_decode_fast(const CodecParams& p, bool rows_word_aligned, d
     const bool tiled = rows_tileable(p, rows_word_aligned);
     switch (p.interleave == ilv_sample ? p.components : 1)
     {
-    case 2:
-        return dispatch_decode_nc<2>(p, tiled, grid, block, stream, jobs);
     case 3:
         return dispatch_decode_nc<3>(p, tiled, grid, block, stream, jobs);
+#if !defined(JLS_DEV_SUBSET) // development builds (tools/dev_sass.sh) instantiate the one- and three-component kernels only
+    case 2:
+        return dispatch_decode_nc<2>(p, tiled, grid, block, stream, jobs);
     case 4:
         return dispatch_decode_nc<4>(p, tiled, grid, block, stream, jobs);
+#endif
     default:
         return dispatch_decode_nc<1>(p, tiled, grid, block, stream, jobs);
     }

@@ -93,6 +93,23 @@ def test_estimated_destination_size(product, reference):
         assert ours.estimated_destination_size() == theirs.estimated_destination_size()
 
 
+def test_estimated_destination_size_covers_narrow_tall_images(product, oracle):
+    """With one restart interval per line the first sample of every line is predicted from 0 and can take a whole
+    LIMIT-bit code word: tall narrow images that the reference squeezes into a few bytes cost 6-10 bytes per line here.
+    The estimate must cover them (sizes from the oracle at restart interval 1, no GPU needed)."""
+    import numpy as np
+
+    for w, h, bits, cc, value in ((1, 10000, 8, 1, 200), (2, 10000, 16, 1, 51234), (1, 3000, 16, 3, 65535), (4, 5000, 12, 1, 4095),
+                                  (3, 2000, 8, 4, 255), (1, 1, 8, 1, 255)):
+        dtype = np.uint8 if bits <= 8 else np.uint16
+        image = np.full((h, w) if cc == 1 else (h, w, cc), value, dtype)
+        ilv = 0 if cc == 1 else 2
+        enc = codec.JpegLSEncoder(product)
+        enc.frame_info(w, h, bits, cc).interleave_mode(ilv)
+        want = oracle.encode_image(image, bits, ilv=ilv, ri=1)
+        assert len(want) <= enc.estimated_destination_size(), (w, h, bits, cc, len(want), enc.estimated_destination_size())
+
+
 def header_summary(lib, stream):
     """Everything read_header exposes, or the error code."""
     try:

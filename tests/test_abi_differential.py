@@ -110,8 +110,11 @@ def random_encoder_sequence(pair, rng, steps):
                 sizes.append(n.value)
             assert codes[0] == codes[1], (codes, pair.log[-12:])
             if codes[0] == 0 and frame:
-                # the reference's bound plus one RSTm per line and component (restart interval 1 by default) and slack
-                assert sizes[0] == sizes[1] + 4 * frame[1] * frame[3] + 8, (sizes, frame)
+                # the reference's bound plus, per line and component (restart interval 1 by default), a whole LIMIT-bit code
+                # word for the first sample, RSTm, padding and a stuffed byte (host/encoder.cpp: estimated_destination_size)
+                bits = max(2, frame[2])
+                per_interval = (2 * (bits + max(8, bits)) + 7) // 8 + 4
+                assert sizes[0] == sizes[1] + per_interval * frame[1] * frame[3] + 8, (sizes, frame)
         pair.written()
 
 
