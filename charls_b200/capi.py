@@ -153,6 +153,10 @@ EXT_SYMBOLS = {
     "charlsx_set_device": (_ERR, [c_int32]),
     "charlsx_jpegls_encoder_set_restart_interval": (_ERR, [_E, c_uint32]),
     "charlsx_jpegls_decoder_get_restart_interval": (_ERR, [_D, POINTER(c_uint32)]),
+    "charlsx_jpegls_encoder_encode_from_buffer_begin": (_ERR, [_E, c_void_p, c_size_t, c_uint32]),
+    "charlsx_jpegls_encoder_encode_end": (_ERR, [_E]),
+    "charlsx_jpegls_decoder_decode_to_buffer_begin": (_ERR, [_D, c_void_p, c_size_t, c_uint32]),
+    "charlsx_jpegls_decoder_decode_end": (_ERR, [_D]),
     "charlsx_batch_create": (c_void_p, []),
     "charlsx_batch_destroy": (None, [c_void_p]),
     "charlsx_batch_encode": (_ERR, [c_void_p, POINTER(BatchParams), POINTER(BatchImage), c_size_t, c_void_p]),

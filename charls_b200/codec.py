@@ -142,6 +142,18 @@ class JpegLSEncoder:
         self.lib.check(self.lib.charls_jpegls_encoder_encode_from_buffer(self._h, addr, size, stride))
         return self.bytes_written()
 
+    # two-part form (extension, include/charls_b200.h): several encoder objects in flight from one thread
+    def encode_begin(self, source, stride: int = 0):
+        addr, size, keep = _as_buffer(source)
+        self._source_in_flight = keep
+        self.lib.check(self.lib.charlsx_jpegls_encoder_encode_from_buffer_begin(self._h, addr, size, stride))
+        return self
+
+    def encode_end(self) -> int:
+        self.lib.check(self.lib.charlsx_jpegls_encoder_encode_end(self._h))
+        self._source_in_flight = None
+        return self.bytes_written()
+
     def encode_components(self, source, source_component_count: int, stride: int = 0) -> int:
         addr, size, _keep = _as_buffer(source)
         self.lib.check(
@@ -263,6 +275,18 @@ class JpegLSDecoder:
         addr, size, _keep = _as_buffer(destination)
         self.lib.check(self.lib.charls_jpegls_decoder_decode_to_buffer(self._h, addr, size, stride))
         return destination
+
+
+    def decode_begin(self, destination: np.ndarray, stride: int = 0):
+        addr, size, keep = _as_buffer(destination)
+        self._destination_in_flight = keep
+        self.lib.check(self.lib.charlsx_jpegls_decoder_decode_to_buffer_begin(self._h, addr, size, stride))
+        return self
+
+    def decode_end(self):
+        self.lib.check(self.lib.charlsx_jpegls_decoder_decode_end(self._h))
+        self._destination_in_flight = None
+        return self
 
 
 # -- convenience helpers ------------------------------------------------------------------------------------------

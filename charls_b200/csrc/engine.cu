@@ -93,8 +93,11 @@ Engine::~Engine()
         if (event)
             cudaEventDestroy(event);
     drop_graphs();
-    for (Buffer* b : {&stage_pixels_[0], &stage_pixels_[1], &stage_streams_[0], &stage_streams_[1]})
-        release(*b);
+    for (Buffer& b : stage_pixels_)
+        release(b);
+    for (Buffer& b : stage_streams_)
+        release(b);
+    delete helper_;
     for (auto& event : in_done_)
         if (event)
             cudaEventDestroy(event);
@@ -511,10 +514,19 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
                                       size_t capacity, size_t& written)
 {
     written = 0;
+    JLS_CHECK(encode_scan_from_host_begin(p, source, stride, destination, capacity));
+    return encode_scan_from_host_end(written);
+}
+
+// Everything of an encode that needs no answer from the device: input copy, kernels, the 32-byte outcome.  Nothing waits.
+int32_t Engine::encode_scan_from_host_begin(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
+                                            size_t capacity)
+{
+    pending_ = Pending{};
     JLS_CHECK(prepare());
     trace_host(0);
     trace_gpu(0);
-    const uint64_t launches_before = thread_kernel_launch_count();
+    pending_.launches_before = thread_kernel_launch_count();
     const size_t row_bytes = row_bytes_of(p);
     const size_t pitch = align_up(row_bytes, 16);
     JLS_CHECK(ensure(pixels_, pitch * static_cast<size_t>(p.height) + 64));
@@ -560,20 +572,34 @@ int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* sourc
     }));
     trace_gpu(2);
     trace_host(1);
+    pending_.active = true;
+    pending_.destination = destination;
+    pending_.capacity = capacity;
+    pending_.direct = direct != nullptr;
+    return 0;
+}
+
+// Waits for the outcome, then fetches the entropy-coded bytes (their count is only known now) and waits for them.
+int32_t Engine::encode_scan_from_host_end(size_t& written)
+{
+    written = 0;
+    if (!pending_.active)
+        return 100; // invalid_operation
+    pending_.active = false;
     JLS_CHECK(wait_for(stream_));
     trace_host(2);
     last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
-    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - pending_.launches_before);
 
     const uint64_t* outcome = static_cast<const uint64_t*>(host_outcomes_.data);
     if (outcome[0] != ~0ULL)
         return static_cast<int32_t>(outcome[0] & 0xFF);
     const uint64_t total = outcome[1];
-    if (total > capacity)
+    if (total > pending_.capacity)
         return err_destination_too_small;
-    if (total != 0 && !direct)
+    if (total != 0 && !pending_.direct)
     {
-        JLS_CUDA(cudaMemcpyAsync(destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
+        JLS_CUDA(cudaMemcpyAsync(pending_.destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
         trace_gpu(3);
         JLS_CHECK(wait_for(stream_));
     }
@@ -598,10 +624,18 @@ int32_t Engine::upload_stream(const uint8_t* host_stream, size_t size)
 int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed)
 {
     consumed = 0;
+    JLS_CHECK(decode_scan_to_host_begin(p, offset, destination, stride));
+    return decode_scan_to_host_end(consumed);
+}
+
+// Kernels, outcome and the copy of the samples to the caller's buffer are all issued here; nothing waits.
+int32_t Engine::decode_scan_to_host_begin(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride)
+{
+    pending_ = Pending{};
     JLS_CHECK(prepare());
     if (offset > uploaded_stream_size_)
         return err_need_more_data;
-    const uint64_t launches_before = thread_kernel_launch_count();
+    pending_.launches_before = thread_kernel_launch_count();
     const size_t remaining = uploaded_stream_size_ - offset;
     const size_t row_bytes = row_bytes_of(p);
     const size_t pitch = align_up(row_bytes, 16);
@@ -647,10 +681,20 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
                                    cudaMemcpyDeviceToHost, stream_));
     trace_gpu(3);
     trace_host(1);
+    pending_.active = true;
+    return 0;
+}
+
+int32_t Engine::decode_scan_to_host_end(size_t& consumed)
+{
+    consumed = 0;
+    if (!pending_.active)
+        return 100; // invalid_operation
+    pending_.active = false;
     JLS_CHECK(wait_for(stream_));
     trace_host(2);
     last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
-    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - pending_.launches_before);
     trace_host(3);
     trace_commit(1);
 
@@ -667,11 +711,22 @@ int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t
 int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
                              size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding)
 {
-    JLS_CHECK(prepare());
     if (count == 0)
-        return 0;
+        return prepare();
+    JLS_CHECK(encode_batch_begin(p, header, header_size, frames, count, stride, user_stream));
+    if (while_coding)
+        JLS_CHECK(while_coding());
+    return encode_batch_end(frames, count, header_size, user_stream);
+}
+
+// Issues the whole batch (job table, kernels, headers and EOI, outcome copy) on `user_stream` or the engine's own stream
+// and returns; encode_batch_end waits and fills in sizes and statuses.
+int32_t Engine::encode_batch_begin(const CodecParams& p, const uint8_t* header, size_t header_size, const BatchFrame* frames,
+                                   size_t count, size_t stride, CUstream_st* user_stream)
+{
+    JLS_CHECK(prepare());
     cudaStream_t stream = user_stream ? user_stream : stream_;
-    const uint64_t launches_before = thread_kernel_launch_count();
+    batch_launches_before_ = thread_kernel_launch_count();
     const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
     if (slot_bytes >= (size_t{1} << 32))
         return 7; // parameter_value_not_supported, see encode_scan_from_host
@@ -703,19 +758,25 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
     JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
     JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                              stream));
-    if (while_coding)
-        JLS_CHECK(while_coding());
+    return 0;
+}
+
+int32_t Engine::encode_batch_end(BatchFrame* frames, size_t count, size_t header_size, CUstream_st* user_stream)
+{
+    cudaStream_t stream = user_stream ? user_stream : stream_;
     JLS_CHECK(wait_for(stream));
     read_coder_time();
-    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - batch_launches_before_);
 
     int32_t first_error = 0;
     const uint64_t* outcomes = static_cast<const uint64_t*>(host_outcomes_.data);
     for (size_t i = 0; i < count; ++i)
     {
         const uint64_t* outcome = outcomes + i * outcome_words;
+        const bool room = frames[i].stream_capacity >= header_size + 2;
+        const size_t capacity = room ? frames[i].stream_capacity - header_size - 2 : 0;
         int32_t status = outcome[0] != ~0ULL ? static_cast<int32_t>(outcome[0] & 0xFF) : 0;
-        if (status == 0 && outcome[1] > jobs[i].stream_out_capacity)
+        if (status == 0 && outcome[1] > capacity)
             status = err_destination_too_small;
         frames[i].status = status;
         frames[i].stream_size = status == 0 ? header_size + static_cast<size_t>(outcome[1]) + 2 : 0;
@@ -728,6 +789,17 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
 // ---------------------------------------------------------------------------------------------------------------------
 // Batch path: host-resident frames, staged through device memory chunk by chunk
 // ---------------------------------------------------------------------------------------------------------------------
+// The pipeline of the host-resident batch calls:
+//
+//   copy_in_  (stream)   H2D chunk j+2 | H2D chunk j+3 | ...
+//   compute   (2 engines) kernels chunk j (this engine) / chunk j+1 (helper engine), alternating, each on its own stream
+//   copy_out_ (stream)   D2H chunk j-1 | D2H chunk j   | ...
+//
+// over `staging_slots` device staging slots.  A chunk is small (a few frames): its kernels take the latency of one line
+// however few frames it holds (~1.3 ms for 4096 samples), so two chunks are coded at the same time on two engines (own
+// scratch buffers, own stream) while two more are being uploaded; the host only ever waits for the OLDEST chunk in flight
+// (it needs the stream sizes before it can issue their copies).  Round 1 coded one chunk at a time on one stream with two
+// slots and reached 52 % of the PCIe bound.
 int32_t Engine::prepare_staging()
 {
     JLS_CHECK(prepare());
@@ -741,19 +813,26 @@ int32_t Engine::prepare_staging()
     for (auto& event : out_done_)
         if (!event)
             JLS_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+    if (!helper_)
+        helper_ = new (std::nothrow) Engine;
+    if (!helper_)
+        return errc_not_enough_memory;
+    JLS_CHECK(helper_->prepare());
     return 0;
 }
 
-// Frames per staging slot.  A chunk's kernels take at least the latency of one line (~1.3 ms for 4096 samples) however few
-// frames it holds, so chunks hold at least six frames (2 ms of PCIe time each way for 16 MB frames); beyond that smaller
-// chunks mean less time to fill and drain the pipeline (about eight chunks per call), and two slots stay below 512 MiB each.
+// Frames per staging slot: enough to amortise the per-chunk host work (a wait, a dozen driver calls), few enough that the
+// pipeline fills and drains quickly and four slots plus two engines' scratch stay small.  CHARLS_B200_HOST_CHUNK overrides.
 size_t Engine::staging_chunk(size_t count, size_t bytes_per_frame) noexcept
 {
-    constexpr size_t slot_budget = size_t{512} << 20;
+    static const size_t forced = [] {
+        const char* value = std::getenv("CHARLS_B200_HOST_CHUNK");
+        return value ? static_cast<size_t>(std::strtoul(value, nullptr, 10)) : size_t{0};
+    }();
+    constexpr size_t slot_budget = size_t{256} << 20;
     size_t largest = slot_budget / (bytes_per_frame ? bytes_per_frame : 1);
     largest = largest < 1 ? 1 : largest > 64 ? 64 : largest;
-    size_t chunk = (count + 7) / 8;
-    chunk = chunk < 6 ? 6 : chunk;
+    size_t chunk = forced ? forced : 4;
     chunk = chunk > largest ? largest : chunk;
     return chunk > count ? count : chunk;
 }
@@ -774,68 +853,84 @@ int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, s
         largest_capacity = frames[i].stream_capacity > largest_capacity ? frames[i].stream_capacity : largest_capacity;
     stream_slot = align_up(stream_slot < largest_capacity ? stream_slot : largest_capacity, 256);
     const size_t chunk = staging_chunk(count, frame_pitch + stream_slot);
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < staging_slots; ++s)
     {
         JLS_CHECK(ensure(stage_pixels_[s], chunk * frame_pitch + 64));
         JLS_CHECK(ensure(stage_streams_[s], chunk * stream_slot + 64));
     }
 
     const size_t chunks = (count + chunk - 1) / chunk;
-    std::vector<BatchFrame> staged(chunk);
+    std::vector<BatchFrame> staged[staging_slots];
+    for (auto& v : staged)
+        v.resize(chunk);
+    const auto frames_in = [&](size_t j) { return (count - j * chunk < chunk) ? count - j * chunk : chunk; };
+    const auto engine_of = [&](size_t j) -> Engine& { return (j & 1U) ? *helper_ : *this; };
+
     const auto upload = [&](size_t j) -> int32_t {
-        const int s = static_cast<int>(j & 1U);
+        const int s = static_cast<int>(j % staging_slots);
         // the slot is free once the stream copies of the chunk that used it before have left it
         JLS_CUDA(cudaStreamWaitEvent(copy_in_, out_done_[s], 0));
-        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+        const size_t first = j * chunk, n = frames_in(j);
         for (size_t k = 0; k < n; ++k)
             JLS_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch, frames[first + k].pixels, frame_bytes,
                                      cudaMemcpyHostToDevice, copy_in_));
         JLS_CUDA(cudaEventRecord(in_done_[s], copy_in_));
         return 0;
     };
-
-    int32_t first_error = 0;
-    JLS_CUDA(cudaEventRecord(out_done_[0], copy_out_)); // both slots start free
-    JLS_CUDA(cudaEventRecord(out_done_[1], copy_out_));
-    JLS_CHECK(upload(0));
-    uint32_t launches = 0;
-    for (size_t j = 0; j < chunks; ++j)
-    {
-        const int s = static_cast<int>(j & 1U);
-        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+    const auto code = [&](size_t j) -> int32_t {
+        const int s = static_cast<int>(j % staging_slots);
+        const size_t first = j * chunk, n = frames_in(j);
         for (size_t k = 0; k < n; ++k)
         {
             const size_t capacity = frames[first + k].stream_capacity < stream_slot ? frames[first + k].stream_capacity : stream_slot;
-            staged[k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
-                                   static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, capacity, 0, 0, 0};
+            staged[s][k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
+                                      static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, capacity, 0, 0, 0};
         }
-        JLS_CUDA(cudaStreamWaitEvent(stream_, in_done_[s], 0));
-        const double t_before = g_trace.enabled ? g_trace.now() : 0.0;
-        // the next chunk's copies are issued behind this chunk's kernels: streams that share a hardware queue run in issue
-        // order, and a copy issued first would hold the kernels back
-        const int32_t status = encode_batch(p, header, header_size, staged.data(), n, stride, stream_,
-                                            [&]() -> int32_t { return j + 1 < chunks ? upload(j + 1) : 0; });
-        if (g_trace.enabled)
-            std::fprintf(stderr, "encode_batch_host chunk %zu/%zu (%zu frames): coded at %.3f ms, waited %.3f ms\n", j, chunks, n,
-                         g_trace.now(), g_trace.now() - t_before);
-        launches += last_launches_;
+        Engine& engine = engine_of(j);
+        JLS_CUDA(cudaStreamWaitEvent(engine.stream_, in_done_[s], 0));
+        return engine.encode_batch_begin(p, header, header_size, staged[s].data(), n, stride, engine.stream_);
+    };
+    int32_t first_error = 0;
+    uint32_t launches = 0;
+    float coder_ms = 0.0F;
+    const auto complete = [&](size_t j) -> int32_t {
+        const int s = static_cast<int>(j % staging_slots);
+        const size_t first = j * chunk, n = frames_in(j);
+        Engine& engine = engine_of(j);
+        const int32_t status = engine.encode_batch_end(staged[s].data(), n, header_size, engine.stream_);
+        launches += engine.last_launches_;
+        coder_ms += engine.last_coder_ms_;
         if (status != 0 && first_error == 0)
             first_error = status;
         for (size_t k = 0; k < n; ++k)
         {
-            frames[first + k].status = staged[k].status;
-            frames[first + k].stream_size = staged[k].stream_size;
-            if (staged[k].status == 0)
-                JLS_CUDA(cudaMemcpyAsync(frames[first + k].stream, staged[k].stream, staged[k].stream_size, cudaMemcpyDeviceToHost,
+            frames[first + k].status = staged[s][k].status;
+            frames[first + k].stream_size = staged[s][k].stream_size;
+            if (staged[s][k].status == 0)
+                JLS_CUDA(cudaMemcpyAsync(frames[first + k].stream, staged[s][k].stream, staged[s][k].stream_size, cudaMemcpyDeviceToHost,
                                          copy_out_));
         }
         JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_));
+        return 0;
+    };
+
+    for (int s = 0; s < staging_slots; ++s)
+        JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_)); // all slots start free
+    JLS_CHECK(upload(0));
+    if (chunks > 1)
+        JLS_CHECK(upload(1));
+    for (size_t j = 0; j < chunks; ++j)
+    {
+        JLS_CHECK(code(j));
+        if (j + 2 < chunks)
+            JLS_CHECK(upload(j + 2));
+        if (j >= 1)
+            JLS_CHECK(complete(j - 1));
     }
-    const double t_drain = g_trace.enabled ? g_trace.now() : 0.0;
+    JLS_CHECK(complete(chunks - 1));
     JLS_CHECK(wait_for(copy_out_));
-    if (g_trace.enabled)
-        std::fprintf(stderr, "encode_batch_host: drained at %.3f ms after %.3f ms\n", g_trace.now(), g_trace.now() - t_drain);
     last_launches_ = launches;
+    last_coder_ms_ = coder_ms;
     return first_error;
 }
 
@@ -852,62 +947,80 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
         stream_slot = frames[i].stream_capacity > stream_slot ? frames[i].stream_capacity : stream_slot;
     stream_slot = align_up(stream_slot + 16, 256);
     const size_t chunk = staging_chunk(count, frame_pitch + stream_slot);
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < staging_slots; ++s)
     {
         JLS_CHECK(ensure(stage_pixels_[s], chunk * frame_pitch + 64));
         JLS_CHECK(ensure(stage_streams_[s], chunk * stream_slot + 64));
     }
 
     const size_t chunks = (count + chunk - 1) / chunk;
-    std::vector<BatchFrame> staged(chunk);
+    std::vector<BatchFrame> staged[staging_slots];
+    for (auto& v : staged)
+        v.resize(chunk);
+    const auto frames_in = [&](size_t j) { return (count - j * chunk < chunk) ? count - j * chunk : chunk; };
+    const auto engine_of = [&](size_t j) -> Engine& { return (j & 1U) ? *helper_ : *this; };
+
     const auto upload = [&](size_t j) -> int32_t {
-        const int s = static_cast<int>(j & 1U);
+        const int s = static_cast<int>(j % staging_slots);
         JLS_CUDA(cudaStreamWaitEvent(copy_in_, out_done_[s], 0));
-        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+        const size_t first = j * chunk, n = frames_in(j);
         for (size_t k = 0; k < n; ++k)
             JLS_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, frames[first + k].stream,
                                      frames[first + k].stream_capacity, cudaMemcpyHostToDevice, copy_in_));
         JLS_CUDA(cudaEventRecord(in_done_[s], copy_in_));
         return 0;
     };
-
-    int32_t first_error = 0;
-    JLS_CUDA(cudaEventRecord(out_done_[0], copy_out_));
-    JLS_CUDA(cudaEventRecord(out_done_[1], copy_out_));
-    JLS_CHECK(upload(0));
-    uint32_t launches = 0;
-    for (size_t j = 0; j < chunks; ++j)
-    {
-        const int s = static_cast<int>(j & 1U);
-        const size_t first = j * chunk, n = (count - first < chunk) ? count - first : chunk;
+    const auto code = [&](size_t j) -> int32_t {
+        const int s = static_cast<int>(j % staging_slots);
+        const size_t first = j * chunk, n = frames_in(j);
         for (size_t k = 0; k < n; ++k)
-            staged[k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
-                                   static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, frames[first + k].stream_capacity, 0, 0,
-                                   frames[first + k].scan_offset};
-        JLS_CUDA(cudaStreamWaitEvent(stream_, in_done_[s], 0));
-        const double t_before = g_trace.enabled ? g_trace.now() : 0.0;
-        const int32_t status =
-            decode_batch(p, staged.data(), n, stride, stream_, [&]() -> int32_t { return j + 1 < chunks ? upload(j + 1) : 0; });
-        if (g_trace.enabled)
-            std::fprintf(stderr, "decode_batch_host chunk %zu/%zu (%zu frames): decoded at %.3f ms, waited %.3f ms\n", j, chunks, n,
-                         g_trace.now(), g_trace.now() - t_before);
-        launches += last_launches_;
+            staged[s][k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
+                                      static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, frames[first + k].stream_capacity, 0, 0,
+                                      frames[first + k].scan_offset};
+        Engine& engine = engine_of(j);
+        JLS_CUDA(cudaStreamWaitEvent(engine.stream_, in_done_[s], 0));
+        return engine.decode_batch_begin(p, staged[s].data(), n, stride, engine.stream_);
+    };
+    int32_t first_error = 0;
+    uint32_t launches = 0;
+    float coder_ms = 0.0F;
+    const auto complete = [&](size_t j) -> int32_t {
+        const int s = static_cast<int>(j % staging_slots);
+        const size_t first = j * chunk, n = frames_in(j);
+        Engine& engine = engine_of(j);
+        const int32_t status = engine.decode_batch_end(staged[s].data(), n, engine.stream_);
+        launches += engine.last_launches_;
+        coder_ms += engine.last_coder_ms_;
         if (status != 0 && first_error == 0)
             first_error = status;
         for (size_t k = 0; k < n; ++k)
         {
-            frames[first + k].status = staged[k].status;
-            frames[first + k].stream_size = staged[k].stream_size;
-            if (staged[k].status == 0)
-                JLS_CUDA(cudaMemcpyAsync(frames[first + k].pixels, staged[k].pixels, frame_bytes, cudaMemcpyDeviceToHost, copy_out_));
+            frames[first + k].status = staged[s][k].status;
+            frames[first + k].stream_size = staged[s][k].stream_size;
+            if (staged[s][k].status == 0)
+                JLS_CUDA(cudaMemcpyAsync(frames[first + k].pixels, staged[s][k].pixels, frame_bytes, cudaMemcpyDeviceToHost, copy_out_));
         }
         JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_));
+        return 0;
+    };
+
+    for (int s = 0; s < staging_slots; ++s)
+        JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_));
+    JLS_CHECK(upload(0));
+    if (chunks > 1)
+        JLS_CHECK(upload(1));
+    for (size_t j = 0; j < chunks; ++j)
+    {
+        JLS_CHECK(code(j));
+        if (j + 2 < chunks)
+            JLS_CHECK(upload(j + 2));
+        if (j >= 1)
+            JLS_CHECK(complete(j - 1));
     }
-    const double t_drain = g_trace.enabled ? g_trace.now() : 0.0;
+    JLS_CHECK(complete(chunks - 1));
     JLS_CHECK(wait_for(copy_out_));
-    if (g_trace.enabled)
-        std::fprintf(stderr, "decode_batch_host: drained at %.3f ms after %.3f ms\n", g_trace.now(), g_trace.now() - t_drain);
     last_launches_ = launches;
+    last_coder_ms_ = coder_ms;
     return first_error;
 }
 
@@ -942,11 +1055,20 @@ int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32
 int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream,
                              const std::function<int32_t()>& while_coding)
 {
-    JLS_CHECK(prepare());
     if (count == 0)
-        return 0;
+        return prepare();
+    JLS_CHECK(decode_batch_begin(p, frames, count, stride, user_stream));
+    if (while_coding)
+        JLS_CHECK(while_coding());
+    return decode_batch_end(frames, count, user_stream);
+}
+
+int32_t Engine::decode_batch_begin(const CodecParams& p, const BatchFrame* frames, size_t count, size_t stride,
+                                   CUstream_st* user_stream)
+{
+    JLS_CHECK(prepare());
     cudaStream_t stream = user_stream ? user_stream : stream_;
-    const uint64_t launches_before = thread_kernel_launch_count();
+    batch_launches_before_ = thread_kernel_launch_count();
 
     size_t max_remaining = 0;
     // the tile kernels keep row offsets of up to three strides in 32 bits (jls_tile.cuh, TileWalk)
@@ -973,11 +1095,15 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
     JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
     JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                              stream));
-    if (while_coding)
-        JLS_CHECK(while_coding());
+    return 0;
+}
+
+int32_t Engine::decode_batch_end(BatchFrame* frames, size_t count, CUstream_st* user_stream)
+{
+    cudaStream_t stream = user_stream ? user_stream : stream_;
     JLS_CHECK(wait_for(stream));
     read_coder_time();
-    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - launches_before);
+    last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - batch_launches_before_);
 
     int32_t first_error = 0;
     const uint64_t* outcomes = static_cast<const uint64_t*>(host_outcomes_.data);

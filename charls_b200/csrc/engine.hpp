@@ -52,6 +52,15 @@ public:
     int32_t encode_scan_from_host(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
                                   size_t capacity, size_t& written);
 
+    // The same call in two halves (charlsx_*_begin / _end): `begin` issues the input copy, the kernels and the outcome copy
+    // and returns without waiting, `end` waits and moves the entropy-coded bytes.  One pending half per engine; a host
+    // thread keeps several codec objects (= engines = CUDA streams) in flight this way.
+    int32_t encode_scan_from_host_begin(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
+                                        size_t capacity);
+    int32_t encode_scan_from_host_end(size_t& written);
+    int32_t decode_scan_to_host_begin(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride);
+    int32_t decode_scan_to_host_end(size_t& consumed);
+
     // Copies a complete JPEG-LS stream to the device once; decode_scan_to_host then works on offsets into it.
     int32_t upload_stream(const uint8_t* host_stream, size_t size);
     // Decodes the scan whose entropy-coded data starts `offset` bytes into the uploaded stream.
@@ -126,6 +135,15 @@ private:
     void read_coder_time() noexcept;
     int32_t wait_for(CUstream_st* stream);
 
+    struct Pending // the half-finished single-image call (begin issued, end not yet called)
+    {
+        bool active{};
+        bool direct{};
+        uint8_t* destination{};
+        size_t capacity{};
+        uint64_t launches_before{};
+    };
+    Pending pending_;
     CUstream_st* stream_{};
     int device_{-1};
     Buffer pixels_, stream_buffer_, slots_, interval_bytes_, interval_offset_, line_scratch_, job_table_, outcomes_,
@@ -140,11 +158,20 @@ private:
     // host-resident batches: staging slots and the two copy streams
     int32_t prepare_staging();
     static size_t staging_chunk(size_t count, size_t bytes_per_frame) noexcept;
-    Buffer stage_pixels_[2], stage_streams_[2];
+    static constexpr int staging_slots = 4;
+    Buffer stage_pixels_[staging_slots], stage_streams_[staging_slots];
     CUstream_st* copy_in_{};
     CUstream_st* copy_out_{};
-    CUevent_st* in_done_[2]{};
-    CUevent_st* out_done_[2]{};
+    CUevent_st* in_done_[staging_slots]{};
+    CUevent_st* out_done_[staging_slots]{};
+    Engine* helper_{}; // second compute engine of the host-batch pipeline (odd chunks), created on first use
+    uint64_t batch_launches_before_{};
+    // the two halves of encode_batch / decode_batch: issue everything, then wait and collect sizes / statuses
+    int32_t encode_batch_begin(const CodecParams& p, const uint8_t* header, size_t header_size, const BatchFrame* frames, size_t count,
+                               size_t stride, CUstream_st* user_stream);
+    int32_t encode_batch_end(BatchFrame* frames, size_t count, size_t header_size, CUstream_st* user_stream);
+    int32_t decode_batch_begin(const CodecParams& p, const BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream);
+    int32_t decode_batch_end(BatchFrame* frames, size_t count, CUstream_st* user_stream);
     // CHARLS_B200_TRACE timeline of the single-image calls (engine.cu: Trace)
     void trace_gpu(int index) noexcept;
     uint8_t* device_view_of(void* pointer) noexcept;

@@ -12,7 +12,15 @@ using namespace jls::host;
 
 struct charls_jpegls_decoder final
 {
-    ~charls_jpegls_decoder() { Engine::release(engine_); }
+    ~charls_jpegls_decoder()
+    {
+        if (deferred_)
+        {
+            size_t ignored = 0;
+            (void)engine().decode_scan_to_host_end(ignored); // the copy into the caller's buffer may still be running
+        }
+        Engine::release(engine_);
+    }
     Engine& engine()
     {
         if (!engine_)
@@ -116,10 +124,12 @@ struct charls_jpegls_decoder final
     }
 
     // reference src/charls_jpegls_decoder.cpp:177-201
-    void decode(uint8_t* destination, size_t destination_size, size_t stride)
+    // `deferred` (charlsx_jpegls_decoder_decode_to_buffer_begin): a frame that is a single scan is only issued here and
+    // decode_end() completes it; frames of several scans need the host between the scans and run to the end here.
+    void decode(uint8_t* destination, size_t destination_size, size_t stride, bool deferred = false)
     {
         check_buffer(destination, destination_size);
-        check_operation(state_ == State::header_read);
+        check_operation(state_ == State::header_read && !deferred_);
         const charls_frame_info& info = reader_.frame_info();
         (void)check_stride_and_destination_size(destination_size, stride); // argument errors come before any device work
         check_status(engine().upload_stream(reader_.source_data(), reader_.source_size()));
@@ -134,6 +144,12 @@ struct charls_jpegls_decoder final
                                                     info.bits_per_sample, static_cast<int32_t>(reader_.scan_component_count()),
                                                     reader_.scan_near_lossless(), ilv, ilv != 0 ? reader_.color_transformation() : 0,
                                                     preset, reader_.restart_interval());
+            if (deferred && component == 0 && reader_.scan_component_count() == reader_.component_count())
+            {
+                check_status(engine().decode_scan_to_host_begin(p, reader_.position(), destination, scan_stride));
+                deferred_ = true;
+                return;
+            }
             size_t consumed = 0;
             check_status(engine().decode_scan_to_host(p, reader_.position(), destination, scan_stride, consumed));
             reader_.advance(consumed);
@@ -145,6 +161,22 @@ struct charls_jpegls_decoder final
             destination_size -= scan_stride * info.height;
             reader_.read_next_start_of_scan();
         }
+        reader_.read_end_of_image();
+        state_ = State::completed;
+    }
+
+    // second half of a deferred decode; a no-op when the first half ran to the end by itself
+    void decode_end()
+    {
+        if (!deferred_)
+        {
+            check_operation(state_ == State::completed);
+            return;
+        }
+        deferred_ = false;
+        size_t consumed = 0;
+        check_status(engine().decode_scan_to_host_end(consumed));
+        reader_.advance(consumed);
         reader_.read_end_of_image();
         state_ = State::completed;
     }
@@ -175,6 +207,7 @@ private:
     State state_{State::initial};
     StreamReader reader_;
     Engine* engine_{}; // borrowed from the pool on first use
+    bool deferred_{};  // decode_to_buffer_begin has issued the scan, decode_end has not been called yet
 };
 
 extern "C" {
@@ -316,6 +349,18 @@ charls_jpegls_errc charls_decoder_get_mapping_table_data(const charls_jpegls_dec
         decoder->reader().mapping_table_data(static_cast<size_t>(mapping_table_index), static_cast<uint8_t*>(mapping_table_data),
                                              mapping_table_size_bytes);
     });
+}
+
+charls_jpegls_errc charlsx_jpegls_decoder_decode_to_buffer_begin(charls_jpegls_decoder* decoder, void* destination_buffer,
+                                                                 size_t destination_size_bytes, uint32_t stride) noexcept
+{
+    return guarded(
+        [&] { check_pointer(decoder)->decode(static_cast<uint8_t*>(destination_buffer), destination_size_bytes, stride, true); });
+}
+
+charls_jpegls_errc charlsx_jpegls_decoder_decode_end(charls_jpegls_decoder* decoder) noexcept
+{
+    return guarded([&] { check_pointer(decoder)->decode_end(); });
 }
 
 charls_jpegls_errc charlsx_jpegls_decoder_get_restart_interval(const charls_jpegls_decoder* decoder, uint32_t* restart_interval) noexcept

@@ -14,7 +14,15 @@ using namespace jls::host;
 
 struct charls_jpegls_encoder final
 {
-    ~charls_jpegls_encoder() { Engine::release(engine_); }
+    ~charls_jpegls_encoder()
+    {
+        if (deferred_components_ != 0)
+        {
+            size_t ignored = 0;
+            (void)engine().encode_scan_from_host_end(ignored); // nothing of this object may stay in flight
+        }
+        Engine::release(engine_);
+    }
     Engine& engine()
     {
         if (!engine_)
@@ -167,7 +175,10 @@ struct charls_jpegls_encoder final
     }
 
     // reference src/charls_jpegls_encoder.cpp:187-236
-    void encode_components(const uint8_t* source, size_t source_size, int32_t source_component_count, size_t stride)
+    // `deferred` (charlsx_jpegls_encoder_encode_from_buffer_begin): a call that makes exactly one scan only issues it;
+    // encode_end() completes it.  Calls that make several scans (planar components) run to the end here.
+    void encode_components(const uint8_t* source, size_t source_size, int32_t source_component_count, size_t stride,
+                           bool deferred = false)
     {
         check_buffer(source, source_size);
         check_can_write();
@@ -211,6 +222,13 @@ struct charls_jpegls_encoder final
         if (interleave_mode_ == 0)
         {
             const size_t plane_bytes = scan_stride * frame_info_.height;
+            if (deferred && source_component_count == 1)
+            {
+                writer_.write_start_of_scan(1, near_lossless_, interleave_mode_);
+                begin_scan(source, scan_stride, 1);
+                deferred_components_ = 1;
+                return;
+            }
             for (int32_t component = 0; component < source_component_count; ++component)
             {
                 writer_.write_start_of_scan(1, near_lossless_, interleave_mode_);
@@ -220,10 +238,31 @@ struct charls_jpegls_encoder final
         else
         {
             writer_.write_start_of_scan(source_component_count, near_lossless_, interleave_mode_);
+            if (deferred)
+            {
+                begin_scan(source, scan_stride, source_component_count);
+                deferred_components_ = source_component_count;
+                return;
+            }
             encode_scan(source, scan_stride, source_component_count);
         }
 
         encoded_component_count_ += source_component_count;
+        if (encoded_component_count_ == frame_info_.component_count)
+            write_end_of_image();
+    }
+
+    // second half of a deferred encode; a no-op when the first half ran to the end by itself
+    void encode_end()
+    {
+        if (deferred_components_ == 0)
+            return;
+        const int32_t components = deferred_components_;
+        deferred_components_ = 0;
+        size_t written = 0;
+        check_status(engine().encode_scan_from_host_end(written));
+        writer_.advance(written);
+        encoded_component_count_ += components;
         if (encoded_component_count_ == frame_info_.component_count)
             write_end_of_image();
     }
@@ -234,8 +273,9 @@ struct charls_jpegls_encoder final
         write_end_of_image();
     }
 
-    void rewind() noexcept
+    void rewind()
     {
+        check_operation(deferred_components_ == 0);
         if (state_ == State::initial)
             return;
         writer_.rewind();
@@ -248,7 +288,10 @@ struct charls_jpegls_encoder final
     void user_preset(const charls_jpegls_pc_parameters& pc) noexcept { user_preset_ = pc; }
 
 private:
-    void check_can_write() const { check_operation(state_ >= State::destination_set && state_ < State::completed); }
+    void check_can_write() const
+    {
+        check_operation(state_ >= State::destination_set && state_ < State::completed && deferred_components_ == 0);
+    }
 
     int32_t effective_maximum_sample_value(int32_t maximum_value) const
     {
@@ -315,6 +358,14 @@ private:
         writer_.advance(written);
     }
 
+    void begin_scan(const uint8_t* source, size_t stride, int32_t component_count)
+    {
+        const CodecParams p = make_codec_params(static_cast<int32_t>(frame_info_.width), static_cast<int32_t>(frame_info_.height),
+                                                frame_info_.bits_per_sample, component_count, near_lossless_, interleave_mode_,
+                                                interleave_mode_ != 0 ? color_transformation_ : 0, preset_, restart_interval_);
+        check_status(engine().encode_scan_from_host_begin(p, source, stride, writer_.remaining_data(), writer_.remaining_size()));
+    }
+
     void write_end_of_image()
     {
         writer_.write_end_of_image((encoding_options_ & 1U) != 0);
@@ -333,6 +384,7 @@ private:
     charls_jpegls_pc_parameters user_preset_{};
     PresetCodingParameters preset_{};
     Engine* engine_{}; // borrowed from the pool on first use
+    int32_t deferred_components_{}; // components of the scan that encode_from_buffer_begin has issued and encode_end completes
 };
 
 extern "C" {
@@ -490,6 +542,20 @@ charls_jpegls_errc charls_jpegls_encoder_rewind(charls_jpegls_encoder* encoder) 
 charls_jpegls_errc charlsx_jpegls_encoder_set_restart_interval(charls_jpegls_encoder* encoder, uint32_t restart_interval) noexcept
 {
     return guarded([&] { check_pointer(encoder)->restart_interval(restart_interval); });
+}
+
+charls_jpegls_errc charlsx_jpegls_encoder_encode_from_buffer_begin(charls_jpegls_encoder* encoder, const void* source_buffer,
+                                                                   size_t source_size_bytes, uint32_t stride) noexcept
+{
+    return guarded([&] {
+        check_pointer(encoder)->encode_components(static_cast<const uint8_t*>(source_buffer), source_size_bytes,
+                                                  encoder->frame().component_count, stride, true);
+    });
+}
+
+charls_jpegls_errc charlsx_jpegls_encoder_encode_end(charls_jpegls_encoder* encoder) noexcept
+{
+    return guarded([&] { check_pointer(encoder)->encode_end(); });
 }
 
 } // extern "C"

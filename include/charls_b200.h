@@ -337,6 +337,26 @@ CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_decoder_get_restart_interval(c
                                                                                uint32_t* restart_interval) CHARLS_B200_NOEXCEPT;
 
 /* Batch interface: all frames share geometry and coding parameters, samples and streams live in DEVICE memory. */
+/* Two-part forms of the hot entry points (no counterpart in the reference, whose calls are synchronous: reference
+ * src/charls_jpegls_encoder.cpp:285-296, src/charls_jpegls_decoder.cpp:177-201).  `_begin` validates like the one-part call,
+ * writes / has read the marker segments and ISSUES the scan on the object's CUDA stream -- input copy, kernels, and for the
+ * decoder the copy of the samples into destination_buffer -- without waiting; `_end` waits for it, moves the entropy-coded
+ * bytes into the destination (encoder) and finishes the object exactly as the one-part call would have (same error codes,
+ * same bytes).  Between the two the caller may start work on OTHER codec objects: that is how one host thread keeps several
+ * images in flight.  Source and destination buffers must stay valid until `_end` returns; no other call on the object is
+ * allowed in between (invalid_operation).  Frames that are coded as several scans (planar components) run to completion
+ * inside `_begin`; `_end` is then a no-op. */
+CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_encoder_encode_from_buffer_begin(charls_jpegls_encoder* encoder,
+                                                                                   const void* source_buffer,
+                                                                                   size_t source_size_bytes,
+                                                                                   uint32_t stride) CHARLS_B200_NOEXCEPT;
+CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_encoder_encode_end(charls_jpegls_encoder* encoder) CHARLS_B200_NOEXCEPT;
+CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_decoder_decode_to_buffer_begin(charls_jpegls_decoder* decoder,
+                                                                                 void* destination_buffer,
+                                                                                 size_t destination_size_bytes,
+                                                                                 uint32_t stride) CHARLS_B200_NOEXCEPT;
+CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_decoder_decode_end(charls_jpegls_decoder* decoder) CHARLS_B200_NOEXCEPT;
+
 typedef struct charlsx_batch_image
 {
     void* pixels;           /* device: samples of the frame (encode: input, decode: output), 16-byte aligned */

@@ -250,3 +250,10 @@ def test_compute_fails_loudly_without_gpu(oracle, product):
     with pytest.raises(CharlsError) as info:
         codec.decode(oracle.encode_image(s_mixed(4, 4, 8), 8), lib=product)
     assert info.value.errc == 200
+    # the two-part forms fail in the first half
+    enc = codec.JpegLSEncoder(product)
+    enc.frame_info(4, 4, 8, 1)
+    enc.destination(np.zeros(4096, np.uint8))
+    with pytest.raises(CharlsError) as info:
+        enc.encode_begin(s_mixed(4, 4, 8))
+    assert info.value.errc == 200

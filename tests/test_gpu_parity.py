@@ -236,6 +236,70 @@ def test_corrupt_streams_never_hang(product, oracle):
     assert agreed >= 0.8 * rejected_by_reference, (agreed, rejected_by_reference)
 
 
+def test_two_part_calls_keep_several_images_in_flight(product, oracle):
+    """charlsx_*_begin / _end: one thread, eight encoder objects issued before the first is completed, then eight decoders
+    the same way; bytes and samples equal the one-part calls' (= the oracle's); calls in between are refused."""
+    from charls_b200.codec import JpegLSDecoder, JpegLSEncoder
+
+    cases = [(s_mixed(40 + 3 * i, 100 + 8 * i, 8, seed=i), 8, 1, 0) for i in range(4)]
+    cases += [(s_smooth(33, 64, 16, 3, seed=9, layout="interleaved"), 16, 3, 2), (s_noise(20, 52, 12, seed=3), 12, 1, 0),
+              (s_mixed(24, 40, 8, 3, seed=5, layout="planar"), 8, 3, 0), (s_smooth(300, 1024, 8, seed=11), 8, 1, 0)]
+    encoders, buffers = [], []
+    for img, bits, cc, ilv in cases:
+        enc = JpegLSEncoder(product)
+        h, w = (img.shape[1], img.shape[2]) if (cc > 1 and ilv == 0) else (img.shape[0], img.shape[1])
+        enc.frame_info(w, h, bits, cc).interleave_mode(ilv)
+        dst = np.zeros(enc.estimated_destination_size() * 2, np.uint8)
+        enc.destination(dst)
+        enc.encode_begin(img)
+        encoders.append(enc)
+        buffers.append(dst)
+    # an object with a scan in flight refuses everything but _end (planar frames ran to the end inside _begin)
+    assert product.charls_jpegls_encoder_write_comment(encoders[0]._h, None, 0) == 100
+    assert product.charls_jpegls_encoder_rewind(encoders[0]._h) == 100
+    streams = []
+    for enc, dst, (img, bits, cc, ilv) in zip(encoders, buffers, cases):
+        n = enc.encode_end()
+        assert enc.encode_end() == n  # a second _end is a no-op
+        streams.append(dst[:n].tobytes())
+        assert payloads(streams[-1]) == payloads(oracle.encode_image(img, bits, ilv=ilv, ri=1))
+        enc.close()
+    decoders, outputs = [], []
+    for s in streams:
+        dec = JpegLSDecoder(product)
+        dec.source(s).read_header()
+        out = np.zeros(dec.destination_size(), np.uint8)
+        dec.decode_begin(out)
+        decoders.append(dec)
+        outputs.append(out)
+    assert product.charls_jpegls_decoder_decode_to_buffer(decoders[0]._h, outputs[0].ctypes.data, outputs[0].nbytes, 0) == 100
+    for dec, out, (img, bits, cc, ilv) in zip(decoders, outputs, cases):
+        dec.decode_end()
+        assert out.tobytes() == np.ascontiguousarray(img).tobytes()
+        dec.close()
+    # an object destroyed between the two halves waits for its work (nothing may write into freed memory afterwards)
+    dec = JpegLSDecoder(product)
+    dec.source(streams[-1]).read_header()
+    out = np.zeros(dec.destination_size(), np.uint8)
+    dec.decode_begin(out)
+    dec.close()
+    assert out.tobytes() == np.ascontiguousarray(cases[-1][0]).tobytes()
+    # errors surface in _end like in the one-part call
+    broken = bytearray(streams[0])
+    broken[len(broken) // 2] ^= 0x40
+    try:
+        codec.decode(bytes(broken), lib=product)
+        want = 0
+    except CharlsError as e:
+        want = e.errc
+    dec = JpegLSDecoder(product)
+    dec.source(bytes(broken)).read_header()
+    out = np.zeros(dec.destination_size(), np.uint8)
+    dec.decode_begin(out)
+    assert product.charlsx_jpegls_decoder_decode_end(dec._h) == want
+    dec.close()
+
+
 def test_instances_on_threads(product, oracle):
     """Distinct encoder / decoder instances are independent (reference: undocumented but de facto)."""
     images = [s_mixed(50, 90, 8, seed=i) for i in range(8)]
