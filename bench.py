@@ -210,6 +210,20 @@ def effective_cpus():
     return n
 
 
+KERNEL_SOURCES = ("jls_kernels.cu", "jls_fast.cuh", "jls_codec.cuh", "jls_tile.cuh", "jls_interval.cuh", "jls_common.h", "jls_params.hpp")
+
+
+def kernel_sources_sha():
+    """Identifies the kernel code a profile was taken with (tools/ncu_traffic.py stores it beside the measured traffic)."""
+    import hashlib
+
+    digest = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "charls_b200", "csrc", name), "rb") as f:
+            digest.update(f.read())
+    return digest.hexdigest()[:16]
+
+
 def host_frames(workload, count, seed=1234):
     """numpy S_smooth frames for the CPU arm (cheap generator shared by `count` frames with different noise)."""
     w, h, bits, cc, _, _, _ = WORKLOADS[workload]
@@ -254,7 +268,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8" if bits <= 8 else "u16", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_step": threads},
+        "config": {"workload": f"{args.workload}: {w}x{h} {bits}-bit x{cc} NEAR={near} ILV={ilv} HP{xf}, no restart markers (the reference "
+                               f"cannot write them), {threads} frames per step = one per host thread",
+                   "frames_per_step": threads, "restart_interval": 0},
         "cpu_baseline": {"value": value, "unit": "MPixels/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -420,6 +436,7 @@ def secondary_workload(torch, dist, lib, device, rank, world, workload, F, steps
         "encode_mpix_s": pixels / (t_enc * 1e-3) / 1e6, "decode_mpix_s": pixels / (t_dec * 1e-3) / 1e6,
         "ratio": raw_bytes / comp_per_frame,
         "roofline_frac": {"encode": algorithmic / (t_enc * 1e-3) / 1e9 / peak, "decode": algorithmic / (t_dec * 1e-3) / 1e9 / peak},
+        "encode_ms": t_enc, "decode_ms": t_dec,
     }
 
 
@@ -543,26 +560,63 @@ def run_gpu_arm(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return world * passes * n * w * h / float(t.item()) / 1e6, sizes_
 
-        # Headline: the two-part calls (charlsx_*_begin / _end -- same objects, same setters, same bytes; the hot call split in
-        # "issue" and "complete") with several codec objects in flight per host thread: the ranks of a box share its cores, and
-        # a thread that waits inside a one-part call has nothing else to do.
+        # Headline: the reference's own calls (charls_jpegls_encoder_encode_from_buffer / charls_jpegls_decoder_decode_to_buffer,
+        # synchronous), one image in flight per host thread.  The ranks of a box share its cores: callers mostly wait for the
+        # GPU, so twice the cores are handed out, but not more (waiters that find no core slow everybody down).
+        threads_one = max(1, min(16, effective_cpus(), max(4, 2 * effective_cpus() // world)))
+        value_one_part, e2e_sizes = measure(threads_one, 1)
+        # Beside it: the two-part forms of the same calls (charlsx_*_begin / _end: "issue" and "complete"), several codec objects
+        # in flight per host thread -- the same throughput from half as many threads
         threads = max(2, min(args.e2e_threads, cpus_per_rank))
         inflight = max(args.e2e_inflight, n // threads) if args.e2e_inflight > 1 else 1
-        value_two_part, e2e_sizes = measure(threads, inflight)
-        # Beside it: the reference's own one-part calls, one image in flight per thread (round 1's e2e)
-        threads_one = max(1, min(16, effective_cpus(), max(4, 2 * effective_cpus() // world)))
-        value_one_part, _ = measure(threads_one, 1)
+        value_two_part, _ = measure(threads, inflight)
         comp = sum(e2e_sizes)
+
+        # What the box can copy: all ranks move the same bytes host->device and device->host at the same time (pinned buffers,
+        # two streams, no kernel).  On the multi-GPU boxes of this pool the GPUs share the host's PCIe / memory path
+        # (tools/pcie_probe_ranks.py: 96 GB/s both ways for one GPU, 104 for two, 120 for four), so this -- not the codec --
+        # bounds e2e from two GPUs on.
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        scratch = torch.empty_like(frames[:n])
+        copy_reps = 3
+
+        def copy_both_ways():
+            with torch.cuda.stream(s_up):
+                scratch.copy_(frames_host, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                out_host.copy_(frames[:n], non_blocking=True)
+
+        copy_both_ways()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(copy_reps):
+            copy_both_ways()
+        s_up.synchronize()
+        s_down.synchronize()
+        c1.record()
+        torch.cuda.synchronize()
+        tc = torch.tensor([c0.elapsed_time(c1) / copy_reps / 1e3], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        copy_gbs_each_way = world * n * raw_bytes / float(tc.item()) / 1e9
+        bytes_each_way_per_pixel = (n * raw_bytes + comp) / (n * w * h)
+        copy_ceiling = copy_gbs_each_way * 1e9 / bytes_each_way_per_pixel / 1e6
+        del scratch
         e2e = {
-            "value": value_two_part, "unit": "MPixels/s",
+            "value": value_one_part, "unit": "MPixels/s",
             "h2d_bytes_per_step": world * passes * (n * raw_bytes + comp), "d2h_bytes_per_step": world * passes * (comp + n * raw_bytes),
-            "frames_per_step": world * passes * n, "pinned_frame_buffers": world * n, "host_threads": threads,
-            "objects_in_flight_per_thread": inflight,
+            "frames_per_step": world * passes * n, "pinned_frame_buffers": world * n, "host_threads": threads_one,
+            "objects_in_flight_per_thread": 1,
             "order": "all frames encoded, then all decoded" if args.e2e_phases else "each frame encoded, then decoded, by one worker",
-            "api": ("charls_jpegls_encoder_* setters + charlsx_jpegls_encoder_encode_from_buffer_begin/_end, charls_jpegls_decoder_* + "
-                    "charlsx_jpegls_decoder_decode_to_buffer_begin/_end, pinned host buffers") if inflight > 1 else
-                   "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
-            "one_part_calls_value": value_one_part, "one_part_calls_host_threads": threads_one,
+            "api": "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
+            "two_part_calls_value": value_two_part, "two_part_calls_host_threads": threads, "two_part_calls_in_flight_per_thread": inflight,
+            "two_part_calls_api": "charlsx_jpegls_encoder_encode_from_buffer_begin/_end + charlsx_jpegls_decoder_decode_to_buffer_begin/_end",
+            "box_copy_gbs_each_way": copy_gbs_each_way, "box_copy_ceiling_mpix_s": copy_ceiling,
+            "frac_of_box_copy_ceiling": value_one_part / copy_ceiling,
+            "box_copy_ceiling_how": "all ranks copy the same pinned buffers up and down at the same time, no kernel (CUDA events, max over ranks)",
         }
 
         # ---- the same host buffers through the host-batch extension: one call per direction from one host thread, the
@@ -595,13 +649,14 @@ def run_gpu_arm(args):
     else:
         peak, peak_kind = 6650.0, "fallback (B200_PROFILING.md)"
 
-    # ---- the metric's other input (16-bit RGB when the headline workload is the 8-bit one, and the other way round)
-    also = None
+    # ---- the metric's other inputs (16-bit RGB and the 12-bit near-lossless frame beside the 8-bit one): measured like `value`
+    also = {}
     if args.also != "none" and args.content == "smooth":
-        other = ("cfg4" if args.workload != "cfg4" else "cfg2") if args.also == "auto" else args.also
+        others = [wl for wl in ("cfg4", "cfg3", "cfg2") if wl != args.workload][:2] if args.also == "auto" else [args.also]
         del frames, streams, decoded
         torch.cuda.empty_cache()
-        also = {other: secondary_workload(torch, dist, lib, device, rank, world, other, max(1, args.frames // 2), max(3, args.steps // 4), peak)}
+        for other in others:
+            also[other] = secondary_workload(torch, dist, lib, device, rank, world, other, max(1, args.frames // 2), max(3, args.steps // 4), peak)
 
     if rank != 0:
         if world > 1:
@@ -611,17 +666,39 @@ def run_gpu_arm(args):
     # ---- roofline of the entropy-coding kernels (algorithmic bytes = raw + compressed)
     algorithmic = F * (raw_bytes + comp_per_frame)
     t_enc, t_dec = float(kernel_ms[0].item()), float(kernel_ms[1].item())
+    # DRAM traffic per launch comes from an ncu capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py together
+    # with a hash of the kernel sources and the commit it was taken at); it is null when the kernels have changed since.
     traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    traffic_fresh = traffic.get("kernels_sha") == kernel_sources_sha()
+    traffic_note = (f"ncu capture at {traffic.get('git', '?')} (profiles/ncu_traffic.json)" if traffic_fresh
+                    else f"null: kernel sources changed since the capture at {traffic.get('git', '?')}")
 
     def roof(name, ms):
         achieved = algorithmic / (ms * 1e-3) / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic.get(f"{name}:{args.workload}:{F}"), "ms_per_launch": ms, "peak_source": peak_kind,
+                "traffic": traffic.get("entries", {}).get(f"{name}:{args.workload}:{F}") if traffic_fresh else None,
+                "traffic_source": traffic_note, "ms_per_launch": ms, "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": algorithmic}
 
     roofs = {"encode": roof("k_encode_tiled", t_enc), "decode": roof("k_decode_tiled", t_dec)}
-    dominant = roofs["encode"] if t_enc >= t_dec else roofs["decode"]
+    dominant = dict(roofs["encode"] if t_enc >= t_dec else roofs["decode"])
+    other_kernel = roofs["decode"] if t_enc >= t_dec else roofs["encode"]
+    dominant["other_kernel"] = other_kernel["kernel"]
+    dominant["other_kernel_frac"] = other_kernel["frac"]
+    dominant["other_kernel_ms_per_launch"] = other_kernel["ms_per_launch"]
+    config_also = {}
+    for name, r in also.items():
+        # flat scalars: the driver's record keeps the scalar members of `config` and `roofline`
+        config_also[f"{name}_workload"] = r["workload"]
+        config_also[f"{name}_value_mpix_s"] = r["value"]
+        config_also[f"{name}_encode_mpix_s"] = r["encode_mpix_s"]
+        config_also[f"{name}_decode_mpix_s"] = r["decode_mpix_s"]
+        config_also[f"{name}_ratio"] = r["ratio"]
+        dominant[f"{name}_encode_frac"] = r["roofline_frac"]["encode"]
+        dominant[f"{name}_decode_frac"] = r["roofline_frac"]["decode"]
+        dominant[f"{name}_encode_ms_per_launch"] = r["encode_ms"]
+        dominant[f"{name}_decode_ms_per_launch"] = r["decode_ms"]
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu and os.path.exists(REF_LIB):
@@ -645,9 +722,10 @@ def run_gpu_arm(args):
         "config": {"workload": workload_name(args), "frames_per_step": world * F, "restart_interval": 1,
                    "compressed_bytes_per_frame": comp_per_frame, "ratio": raw_bytes / comp_per_frame,
                    "cache": f"inputs larger than L2: {F * raw_bytes / 1e6:.0f} MB raw + {F * comp_per_frame / 1e6:.0f} MB streams per GPU vs 126 MB L2",
-                   "sharding": "frames split across ranks, no data-path collective; NCCL all_gather of stream sizes only"},
+                   "sharding": "frames split across ranks, no data-path collective; NCCL all_gather of stream sizes only",
+                   **config_also},
         "encode_mpix_s": world * F * w * h / (t_enc * 1e-3) / 1e6, "decode_mpix_s": world * F * w * h / (t_dec * 1e-3) / 1e6,
-        "roofline": dominant, "roofline_all": roofs, "cpu_baseline": cpu_baseline, "e2e": e2e, "also": also, "clocks": clocks,
+        "roofline": dominant, "roofline_all": roofs, "cpu_baseline": cpu_baseline, "e2e": e2e, "also": also or None, "clocks": clocks,
         "gpu_launches": int(launches_after.value - launches_before.value),
     }
     print(json.dumps(out))

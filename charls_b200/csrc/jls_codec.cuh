@@ -478,6 +478,11 @@ struct BitReader
     uint32_t shift;       // 8 * (byte offset of the next unread byte inside *wptr)
     const uint8_t* pos;   // next unread byte
     const uint8_t* end;
+    // Bits of the last code word if it was one the reference decodes through its 8-bit look-up table (a regular-mode Golomb
+    // code of at most 8 bits, reference src/scan_decoder_core.hpp:46-52), else 255.  The reference peeks a whole byte for
+    // those and never checks that all bits of the code it then skips were valid (src/scan_decoder.hpp:144-152, 58-64): the
+    // last code word of an interval may end in up to seven zero bits that are not in the stream (interval_end_status).
+    int32_t last_code_bits;
 
     JLS_HD uint32_t load_word(const uint32_t* w) const
     {
@@ -492,6 +497,7 @@ struct BitReader
         prev_ff = false;
         pos = begin;
         end = end_;
+        last_code_bits = 255;
         const uintptr_t address = reinterpret_cast<uintptr_t>(begin);
         wptr = reinterpret_cast<const uint32_t*>(address & ~static_cast<uintptr_t>(3));
         shift = static_cast<uint32_t>(address & 3U) * 8U;
@@ -553,6 +559,7 @@ struct BitReader
 
     // True when bits beyond the end of the interval were consumed (the reference throws invalid_data when it runs dry).
     JLS_HD bool overrun() const { return valid < virtual_bits; }
+    JLS_HD int32_t overrun_bits() const { return virtual_bits - valid; }
 
     // Whole unread bytes left in the interval after the last decoded symbol.
     JLS_HD int64_t unread_bytes() const
@@ -588,7 +595,11 @@ struct BitReader
             }
         }
         if (zeros < limit - qbpp - 1)
+        {
+            last_code_bits = zeros + 1 + k <= 8 ? zeros + 1 + k : 255; // callers in run mode overwrite it with 255
             return k == 0 ? zeros : (zeros << k) + static_cast<int32_t>(read(k));
+        }
+        last_code_bits = 255;
         return static_cast<int32_t>(read(qbpp)) + 1;
     }
 };
@@ -638,6 +649,7 @@ JLS_HD int32_t decode_run_length(BitReader& br, int32_t& run_index, int32_t pixe
         if (j > 0)
             index += static_cast<int32_t>(br.read(j));
     }
+    br.last_code_bits = 255; // run-length bits are read one by one, each with its own validity check (reference read_bit)
     return index > pixel_count ? -1 : index;
 }
 
@@ -658,6 +670,7 @@ JLS_HD int32_t decode_run_interruption_error(const CodecParams& p, BitReader& br
 {
     const int32_t k = run_golomb_parameter(c, ri_type);
     const int32_t e_mapped = br.get_golomb(k, p.limit - run_order(run_index) - 1, p.qbpp, bad);
+    br.last_code_bits = 255; // no look-up table on this path (reference src/scan_decoder.hpp:113-125: every part checked)
     const int32_t e = run_error_value(c, e_mapped + ri_type, k);
     update_run_context(c, e, e_mapped, ri_type, p.reset);
     return e;

@@ -676,6 +676,8 @@ struct FastReaderT
                           // waits for the load its own first word has just issued; the one-component decoders rarely take
                           // two words and lose 2 % to the extra move, so they stay at DEPTH 1
     uint32_t shift;       // 8 * (offset of the next byte inside *wptr)
+    int32_t last_code_bits; // length of the last code word if it was a regular-mode Golomb code without escape, else 255
+                            // (BitReader::last_code_bits, interval_end_status: the reference's look-up table tail)
 
     static constexpr int32_t full_mark = 96; // a refill appends words while valid <= full_mark
 
@@ -695,6 +697,7 @@ struct FastReaderT
         shift = static_cast<uint32_t>(offset) * 8U;
         guard = remaining - (4 - offset);
         bad = 0;
+        last_code_bits = 255;
         cur = remaining > 0 ? *wptr : 0U;
         ahead = guard > 0 ? wptr[1] : 0U;
         ahead2 = DEPTH == 2 && guard > 4 ? wptr[2] : 0U;
@@ -839,6 +842,7 @@ struct FastReaderT
     }
 
     JLS_HD bool overrun() const { return valid < virtual_bits; }
+    JLS_HD int32_t overrun_bits() const { return virtual_bits - valid; }
 
     // true when bits that were not consumed are not all zero
     JLS_HD bool residue() const { return (c3 | c2 | c1 | c0) != 0; }
@@ -869,7 +873,8 @@ struct FastReaderT
         {
             // not an escape, and the code word (z + 1 + k <= steady_bits bits) is valid and sits in c3
             const uint32_t remainder = shr_sat(shl_sat(top, static_cast<uint32_t>(z + 1)), static_cast<uint32_t>(32 - k));
-            consume(z + 1 + k);
+            last_code_bits = z + 1 + k;
+            consume(last_code_bits);
             return (z << k) + static_cast<int32_t>(remainder);
         }
         const int32_t value = get_golomb(h, k, escape);
@@ -888,9 +893,11 @@ struct FastReaderT
         {
             // not an escape and the whole code word (z + 1 + k bits) sits in the top 32 bits (valid > 32)
             const uint32_t remainder = shr_sat(shl_sat(top, static_cast<uint32_t>(z + 1)), static_cast<uint32_t>(32 - k));
-            consume(z + 1 + k);
+            last_code_bits = z + 1 + k;
+            consume(last_code_bits);
             return (z << k) + static_cast<int32_t>(remainder);
         }
+        last_code_bits = 255; // longer than 32 bits or an escape: not in the reference's look-up table
         int32_t zeros = 0;
         for (;;)
         {
@@ -938,6 +945,7 @@ JLS_HD int32_t fast_decode_run_length(Reader& br, int32_t& run_index, int32_t pi
         if (j > 0)
             index += static_cast<int32_t>(br.read(j));
     }
+    br.last_code_bits = 255;
     return index > pixel_count ? -1 : index;
 }
 
@@ -1319,6 +1327,7 @@ struct FastLineDecoder : FastLineState<NC, LUT_MODE, DEPTH>
             const int32_t ri_type = NC == 1 ? 1 : 0;
             const int32_t k = run_golomb_parameter(c, ri_type);
             const int32_t e_mapped = br.get_golomb(h, k, h.limit - run_order(this->run_index) - 1 - h.qbpp - 1);
+            br.last_code_bits = 255;
             const int32_t e = run_error_value(c, e_mapped + ri_type, k);
             update_run_context(c, e, e_mapped, ri_type, h.reset);
             if (NC == 1)

@@ -145,8 +145,19 @@ template<typename Reader>
 JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool bad, uint32_t interval,
                                    bool closing_marker_found = true)
 {
-    if (bad || br.overrun())
+    if (bad)
         return err_invalid_data;
+    if (br.overrun())
+    {
+        // Bits beyond the end of the interval were consumed.  The reference throws invalid_data when it needs bits and finds
+        // none -- except for the tail of a code word it took from its 8-bit look-up table: it peeks a byte (missing bits read
+        // as zero, src/scan_decoder.hpp:144-152), skips the code's length without looking at valid_bits_ (:58-64), and if that
+        // was the interval's last symbol nothing ever asks for bits again (restart marker and end_scan read bytes, :71-89,
+        // 237-243).  At least one bit of the code must be real (fill_read_cache throws on an empty cache, :272-284).
+        const int32_t missing = br.overrun_bits();
+        if (!(br.last_code_bits <= 8 && missing < br.last_code_bits))
+            return err_invalid_data;
+    }
     if (!closing_marker_found)
     {
         // The data ends without a marker.  The reference's read pointer runs at most one cache (8 bytes) ahead of the

@@ -233,6 +233,8 @@ def test_corrupt_streams_never_hang(product, oracle):
     # Random bit flips inside a line: the reference notices some of them only through where its 64-bit read cache
     # happens to stop (src/scan_decoder.hpp:335-349); we do not model the cache fill schedule, so a flip that leaves a few
     # stray bytes in front of a restart marker may pass here and fail there.  Everything else must agree.
+    # (the exact accounting of such streams is test_damaged_walk_against_the_reference: 0 exceptions to "the reference accepts
+    # => we accept", and a pinned count the other way)
     assert agreed >= 0.8 * rejected_by_reference, (agreed, rejected_by_reference)
 
 
@@ -298,6 +300,26 @@ def test_two_part_calls_keep_several_images_in_flight(product, oracle):
     dec.decode_begin(out)
     assert product.charlsx_jpegls_decoder_decode_end(dec._h) == want
     dec.close()
+
+
+def test_damaged_walk_against_the_reference(product, oracle):
+    """The 1620 damaged scans of tests/damaged_walk.py through the kernels (C ABI): reference accepts => we accept with
+    identical samples, 0 exceptions; accepted although the reference rejects: exactly the pinned count."""
+    from tests import damaged_walk
+
+    if not have_reference_build():
+        pytest.skip("oracle/_ref/libcharls_ref.so not built")
+
+    def ours(stream, data, img, sp):
+        try:
+            px, _, _ = codec.decode(stream, lib=product)
+            return px
+        except CharlsError:
+            return None
+
+    accepts, extra = damaged_walk.run_walk(oracle, reference_library(), ours)
+    assert accepts == damaged_walk.EXPECTED_REFERENCE_ACCEPTS
+    assert extra == damaged_walk.EXPECTED_ACCEPTED_THOUGH_REFERENCE_REJECTS
 
 
 def test_instances_on_threads(product, oracle):

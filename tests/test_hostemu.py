@@ -178,3 +178,20 @@ def test_damaged_lines_multi_component(oracle, hostemu):
                 accepted += 1
                 assert n_ours == n_oracle and np.array_equal(got, want), (bits, cc, trial)
     assert checked == 160 and accepted > 0
+
+
+def test_damaged_walk_against_the_reference(oracle, hostemu, reference):
+    """1620 damaged scans through the kernels' codec code on the host (tests/damaged_walk.py): everything the reference
+    accepts is accepted with identical samples; the set it rejects and we accept has exactly the known size."""
+    from tests import damaged_walk
+
+    params = {}
+
+    def ours(stream, data, img, sp):
+        hp = params.setdefault(id(sp), hostemu.params(sp))
+        out = np.zeros_like(img)
+        return out if hostemu.decode(hp, data + b"\xff\xd9", out, False) >= 0 else None
+
+    accepts, extra = damaged_walk.run_walk(oracle, reference, ours)
+    assert accepts == damaged_walk.EXPECTED_REFERENCE_ACCEPTS
+    assert extra == damaged_walk.EXPECTED_ACCEPTED_THOUGH_REFERENCE_REJECTS

@@ -13,22 +13,13 @@ import torch.distributed as dist
 
 
 def numa_node_of_gpu(index):
+    """(NUMA node or -1, PCI address) of a GPU; virtual machines often expose neither a node nor more than one node."""
     try:
-        bus = torch.cuda.get_device_properties(index).pci_bus_id  # newer torch
-    except AttributeError:
-        bus = None
-    if bus is None:
-        import subprocess
-
-        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
-        bus = out
-    bus = bus.lower()
-    if len(bus.split(":")[0]) == 8:
-        bus = bus[4:]
-    try:
+        props = torch.cuda.get_device_properties(index)
+        bus = f"{int(props.pci_domain_id):04x}:{int(props.pci_bus_id):02x}:{int(props.pci_device_id):02x}.0"
         return int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read()), bus
-    except OSError:
-        return -1, bus
+    except Exception as e:  # noqa: BLE001 - a probe must not die on a missing sysfs entry
+        return -1, f"unknown ({type(e).__name__})"
 
 
 def cpus_of_node(node):
