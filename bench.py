@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--also", default="auto", choices=["auto", "none"] + sorted(WORKLOADS),
                     help="second workload reported under \"also\" (auto: cfg4 = 16-bit RGB beside cfg2, the metric names both)")
+    ap.add_argument("--restart-interval", type=int, default=1,
+                    help="lines per restart interval; 1 = every line an independent work item (the design point), 0 = none: the "
+                         "streams the reference itself writes, one CUDA thread per scan (the general path)")
     ap.add_argument("--content", default="smooth", choices=["smooth", "noise", "flat"],
                     help="smooth = S_smooth (the metric's input); noise (uniform, incompressible) and flat (all zero, pure run "
                          "mode) bracket it (SURVEY.md 8d)")
@@ -279,7 +282,7 @@ def run_reference_arm(args):
 def workload_name(args):
     w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
     content = "" if args.content == "smooth" else f", content={args.content}"
-    return (f"{args.workload}: {w}x{h} {bits}-bit x{cc} NEAR={near} ILV={ilv} HP{xf} restart-interval=1, "
+    return (f"{args.workload}: {w}x{h} {bits}-bit x{cc} NEAR={near} ILV={ilv} HP{xf} restart-interval={args.restart_interval}, "
             f"{args.frames} frames per GPU per step{content}")
 
 
@@ -462,7 +465,8 @@ def run_gpu_arm(args):
     w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
     F = args.frames
     frames = make_frames(torch, device, F, args.workload, first_seed=1234 + rank * F, content=args.content)
-    codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=1, lib=lib)
+    codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf,
+                       restart_interval=args.restart_interval, lib=lib)
     if args.content == "noise":
         codec.stream_capacity *= 2  # incompressible input expands (about 9.5 bits per 8-bit sample)
     streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
@@ -681,7 +685,9 @@ def run_gpu_arm(args):
                 "traffic_source": traffic_note, "ms_per_launch": ms, "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": algorithmic}
 
-    roofs = {"encode": roof("k_encode_tiled", t_enc), "decode": roof("k_decode_tiled", t_dec)}
+    fast = args.restart_interval == 1
+    roofs = {"encode": roof("k_encode_tiled" if fast else "k_encode_general", t_enc),
+             "decode": roof("k_decode_tiled" if fast else "k_decode_general", t_dec)}
     dominant = dict(roofs["encode"] if t_enc >= t_dec else roofs["decode"])
     other_kernel = roofs["decode"] if t_enc >= t_dec else roofs["encode"]
     dominant["other_kernel"] = other_kernel["kernel"]
@@ -719,7 +725,7 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": "MPixels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8" if bits <= 8 else "u16", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_step": world * F, "restart_interval": 1,
+        "config": {"workload": workload_name(args), "frames_per_step": world * F, "restart_interval": args.restart_interval,
                    "compressed_bytes_per_frame": comp_per_frame, "ratio": raw_bytes / comp_per_frame,
                    "cache": f"inputs larger than L2: {F * raw_bytes / 1e6:.0f} MB raw + {F * comp_per_frame / 1e6:.0f} MB streams per GPU vs 126 MB L2",
                    "sharding": "frames split across ranks, no data-path collective; NCCL all_gather of stream sizes only",

@@ -50,6 +50,10 @@
 #ifndef JLS_FMA_ADDS
 #define JLS_FMA_ADDS 1
 #endif
+// 1: the one-component 8-bit decoders top their read window up every 8 samples instead of every 4 (FastLineDecoder)
+#ifndef JLS_TOP_UP_8
+#define JLS_TOP_UP_8 1
+#endif
 
 namespace jls {
 
@@ -223,6 +227,16 @@ JLS_HD int32_t fast_error_value(const HotParams& h, int32_t e)
 JLS_HD int32_t fast_clamp(const HotParams& h, int32_t v) // == correct_prediction: v in [0, maxval] or the nearer bound
 {
     return imin(imax(v, 0), h.maxval);
+}
+
+// three-input maximum: one VIMNMX3 on sm_100a
+JLS_HD uint32_t umax3(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimax3_u32(a, b, c);
+#else
+    return umax(umax(a, b), c);
+#endif
 }
 
 // max(min(a + b, high), 0) -- one VIADDMNMX.RELU on sm_100a
@@ -568,7 +582,10 @@ struct FastWriter
             // mapped = high << k | low and the code word is 1 << k | low: flip the bits in which high differs from 1
             uint32_t value = static_cast<uint32_t>(mapped) ^ (static_cast<uint32_t>(high ^ 1) << k);
             int32_t length = add_fma(h, high, add_fma(h, k, 1));
-            if (JLS_UNLIKELY(high >= imin(escape, MODE - k))) // an escape, or longer than MODE bits
+            // an escape (high >= escape), or longer than MODE bits: one compare -- a code word of at most min(MODE, escape) bits
+            // has fewer than `escape` zeros in front (the few legal code words between the two bounds take the long form's
+            // path as well; it writes them just the same), and the bound is loop invariant
+            if (JLS_UNLIKELY(length > imin(MODE, escape)))
             {
                 put_golomb<write_wide>(h, k, mapped, escape);
                 drain<MODE>();
@@ -659,7 +676,9 @@ JLS_HD void fast_encode_run_length(FastWriter& bw, int32_t& run_index, int32_t r
 // of the warp at the same time, and the refill inside get_golomb()/read() is a rarely taken fall-back.  With a 64-bit
 // window some lane of the warp needed a word at nearly every symbol and the whole warp paid for the refill each time.
 // ---------------------------------------------------------------------------------------------------------------------
-template<int DEPTH>
+// STEADY_BITS: the longest code word of the unchecked path (get_golomb_steady); (full_mark + 1) / STEADY_BITS - 1 symbols fit
+// between two top-ups: 24 bits -> 4 symbols, 12 bits -> 8 symbols.
+template<int DEPTH, int STEADY_BITS = 24>
 struct FastReaderT
 {
     uint32_t c3, c2, c1, c0; // the window, left aligned: c3 holds the next bits
@@ -858,8 +877,9 @@ struct FastReaderT
     // tops the window up to > full_mark bits at least every `steady_symbols` symbols, the straight-line path below
     // only takes code words of up to `steady_bits` bits (full_mark + 1 - 4 * 24 >= 24), and every other way of
     // consuming bits (long code words, run mode) ends with a top_up() of its own.
-    static constexpr int32_t steady_bits = 24;
-    static constexpr int32_t steady_symbols = 4;
+    static constexpr int32_t steady_bits = STEADY_BITS;
+    static constexpr int32_t steady_symbols = (full_mark + 1) / STEADY_BITS; // 4 (97 - 4 * 24 >= 0 ...) or 8
+    static_assert(full_mark + 1 - (steady_symbols - 1) * steady_bits >= steady_bits, "the last symbol of a group finds its bits");
 
     JLS_HD int32_t get_golomb_steady(const HotParams& h, int32_t k, int32_t escape)
     {
@@ -869,12 +889,14 @@ struct FastReaderT
 #endif
         const uint32_t top = c3;
         const int32_t z = clz32(top);
-        if (JLS_LIKELY(z < imin(escape, steady_bits - k)))
+        const int32_t length = z + 1 + k;
+        if (JLS_LIKELY(length <= imin(steady_bits, escape)))
         {
-            // not an escape, and the code word (z + 1 + k <= steady_bits bits) is valid and sits in c3
+            // not an escape (z < length <= escape), and the code word (at most steady_bits bits) is valid and sits in c3; one
+            // compare against a loop-invariant bound (see FastWriter::put_golomb)
             const uint32_t remainder = shr_sat(shl_sat(top, static_cast<uint32_t>(z + 1)), static_cast<uint32_t>(32 - k));
-            last_code_bits = z + 1 + k;
-            consume(last_code_bits);
+            last_code_bits = length;
+            consume(length);
             return (z << k) + static_cast<int32_t>(remainder);
         }
         const int32_t value = get_golomb(h, k, escape);
@@ -1004,6 +1026,10 @@ struct FastLineState
 #endif
     }
 
+    // Scalar lines reach regular mode only with Ra > NEAR, i.e. never in context 0: callers may pass a `ctx` that points
+    // one row in front of a four-row array (the tile kernels do: 512 bytes of shared memory per block less).
+    static constexpr int32_t first_context = NC == 1 ? 1 : 0;
+
     JLS_HD void begin_interval(const HotParams& h, RegularContext* ctx, int32_t stride)
     {
         contexts = ctx;
@@ -1013,12 +1039,12 @@ struct FastLineState
         // slots per pixel) instead of holding it in a register.  A volatile round trip through the thread's own context
         // slot makes the value opaque.
         static_assert(sizeof(RegularContext) == 16, "one context is one 16-byte shared-memory access");
-        volatile uint32_t* own_slot = reinterpret_cast<volatile uint32_t*>(ctx);
+        volatile uint32_t* own_slot = reinterpret_cast<volatile uint32_t*>(ctx + first_context * stride);
         *own_slot = static_cast<uint32_t>(__cvta_generic_to_shared(ctx));
         context_base = *own_slot;
 #endif
         const RegularContext initial = {h.a_init, 0, 0, 1};
-        for (int32_t q = 0; q < 5; ++q)
+        for (int32_t q = first_context; q < 5; ++q)
             store_context(q, initial);
         cached = initial;
         cached_index = 4;
@@ -1264,7 +1290,11 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE, DEPTH>
 template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, int DEPTH = 0>
 struct FastLineDecoder : FastLineState<NC, LUT_MODE, DEPTH>
 {
-    FastReaderT<NC == 3 ? JLS_READER_DEPTH_NC3 : 1> br;
+    // One-component lines in 8-bit containers code a few bits per sample: eight samples between two top-ups with code words
+    // of up to 12 bits on the unchecked path (a top-up costs the warp ~35 instructions whether one lane or all need a word);
+    // everything else keeps four samples of up to 24 bits.  JLS_TOP_UP_8 = 0 switches back (A/B).
+    static constexpr bool long_cadence = JLS_TOP_UP_8 && NC == 1 && LUT_MODE == lut_full;
+    FastReaderT<NC == 3 ? JLS_READER_DEPTH_NC3 : 1, long_cadence ? 12 : 24> br;
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one
     // register and one test on the regular-mode path
     int32_t pending;
@@ -1308,12 +1338,12 @@ struct FastLineDecoder : FastLineState<NC, LUT_MODE, DEPTH>
         // scaled so that its bound is sanity_limit and goes into a running maximum.  k <= 31 and |e| < 2^22 on every
         // path (24 or `escape` zeros at most, shifted by k <= 15, or k >= 16 which trips the limit by itself), so the
         // products cannot wrap.
-        const uint32_t marks = umax(static_cast<uint32_t>(k) << 20, static_cast<uint32_t>(iabs(e)) << 8);
+        const uint32_t mark_k = static_cast<uint32_t>(k) << 20, mark_e = static_cast<uint32_t>(iabs(e)) << 8;
         // Lossless: the context's own check (A >= 2^24 after the update) never fires first.  |e| <= 65535 puts the A before
         // the update above 2^24 - 2^16, and N <= RESET <= 255 then gives k >= 16 for this very symbol (255 << 15 < 2^24 -
         // 2^16): the k mark has tripped already.  |B| stays below RESET + 65536.  Near-lossless keeps the mark for B.
         const uint32_t water = this->template update<LOSSLESS>(h, e);
-        high_water = LOSSLESS ? umax(high_water, marks) : umax(umax(high_water, marks), water);
+        high_water = LOSSLESS ? umax3(high_water, mark_k, mark_e) : umax(umax3(high_water, mark_k, mark_e), water);
         return fast_reconstruct<LOSSLESS>(h, pv, negative ? -e : e);
     }
 
@@ -1341,7 +1371,7 @@ struct FastLineDecoder : FastLineState<NC, LUT_MODE, DEPTH>
     }
 
     // pixels between two top_up() calls of the pixel loop (FastReader::steady_symbols regular-mode symbols at most)
-    static constexpr int32_t pixels_per_top_up = NC == 1 ? 4 : NC == 2 ? 2 : 1;
+    static constexpr int32_t pixels_per_top_up = long_cadence ? 8 : NC == 1 ? 4 : NC == 2 ? 2 : 1;
 
     // a pixel that belongs to a run, ends one or starts one
     JLS_HD void run_mode_pixel(const HotParams& h, int32_t remaining)

@@ -30,6 +30,15 @@ namespace {
 #if !defined(JLS_FAST_BLOCK_THREADS)
 #define JLS_FAST_BLOCK_THREADS 32
 #endif
+// Pixel loop bodies written out per drain / top-up group for the full-depth one-component kernels.  Measured on cfg2 (A/B on
+// one box, profiles/r2_notes.md): encoder 6.27 -> 6.02 ms, decoder 7.17 -> 7.67 ms (its body is four times the encoder's
+// size and no longer sits well in the instruction caches) -- so the encoder unrolls and the decoder does not.
+#if !defined(JLS_UNROLL_ENCODER)
+#define JLS_UNROLL_ENCODER 1
+#endif
+#if !defined(JLS_UNROLL_DECODER)
+#define JLS_UNROLL_DECODER 0
+#endif
 constexpr int fast_block_threads = JLS_FAST_BLOCK_THREADS;
 constexpr int general_block_threads = 32;
 
@@ -102,25 +111,39 @@ __device__ __forceinline__ void store_shared_sample(uint32_t address, int32_t in
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(address + 2U * static_cast<uint32_t>(index)), "r"(value) : "memory");
 }
 
-template<int NC>
+#if !defined(JLS_NARROW_TILES)
+#define JLS_NARROW_TILES 1
+#endif
+// ENCODER: the encoder double-buffers its tiles; 32-byte tiles for one-component lines (and four instead of five context
+// rows) bring a block's shared memory under the 7 KB that let 32 blocks live on an SM, 48-byte tiles take the
+// three-component encoders from 20 to 27 blocks (JLS_NARROW_TILES).
+template<int NC, typename S = uint16_t, bool ENCODER = false>
 struct TileShape
 {
-    static constexpr int words = NC == 3 ? 24 : 16; // 96 bytes hold whole pixels for 3 x 8 and 3 x 16 bit
+    // 96 (48) bytes hold whole pixels for 3 x 8 and 3 x 16 bit
+    static constexpr int words = NC == 3 ? ((JLS_NARROW_TILES && ENCODER) ? 12 : 24)
+                                         : (JLS_NARROW_TILES && ENCODER && NC == 1) ? 8 : 16;
     static constexpr int stride_words = words + 1;
 };
 
 // DEPTH = bits per sample when lossless data fills its container (8 in uint8_t, 16 in uint16_t): depth, MAXVAL and the
 // sign extension of the error value become immediates and no sample needs masking; 0 = any depth (h.bits).
+// One-component encoders are asked to fit 32 blocks on an SM (64 registers; shared memory: see TileShape), the others keep
+// what ptxas picks (a cap costs the three-component encoders spills, profiles/r1_notes.md).
+#if !defined(JLS_ENCODE_MIN_BLOCKS_NC1)
+#define JLS_ENCODE_MIN_BLOCKS_NC1 32
+#endif
 template<int NC, bool LOSSLESS, typename S, int DEPTH>
-__global__ void __launch_bounds__(fast_block_threads)
+__global__ void __launch_bounds__(fast_block_threads, NC == 1 ? JLS_ENCODE_MIN_BLOCKS_NC1 : NC == 3 ? 26 : 28)
     k_encode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
-    constexpr int TW = TileShape<NC>::words, SW = TileShape<NC>::stride_words;
+    constexpr int TW = TileShape<NC, S, true>::words, SW = TileShape<NC, S, true>::stride_words;
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
+    constexpr int first_context = NC == 1 ? 1 : 0; // scalar lines never use context 0 (FastLineState::first_context)
     // Two tile buffers: the next tile is in flight while this one is coded.  (One buffer and a wait per tile leaves room
     // for more resident blocks -- 31 instead of 21 for three-component pixels -- and measured 3 % slower.)
-    __shared__ RegularContext contexts[5 * fast_block_threads];
+    __shared__ RegularContext contexts[(5 - first_context) * fast_block_threads];
     __shared__ uint32_t tiles[warps][2][32 * SW];
     extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
@@ -151,15 +174,21 @@ __global__ void __launch_bounds__(fast_block_threads)
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     if (DEPTH != 0)
     {
+        // lossless at full depth: RANGE = 2^DEPTH, qbpp = DEPTH, LIMIT = 2 (DEPTH + max(8, DEPTH)) (make_codec_params)
         h.bits = DEPTH;
         h.maxval = (1 << DEPTH) - 1;
+        h.qbpp = DEPTH;
+        h.limit = 2 * (DEPTH + (DEPTH > 8 ? DEPTH : 8));
+        h.escape = h.limit - DEPTH - 1;
     }
     // deferred flushing unless nearly every sample fills a word anyway (lossless 16-bit data)
     FastLineEncoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, writer_mode<NC, LOSSLESS, S>, DEPTH> enc;
     constexpr int32_t drain_mask = decltype(enc)::pixels_per_drain - 1;
+    // JLS_UNROLL_ENCODER: the pixel loop's body written out once per pixel of a drain group (full-depth one-component kernels)
+    constexpr bool unrolled_groups = JLS_UNROLL_ENCODER && NC == 1 && DEPTH != 0 && drain_mask > 0;
     uint8_t* slot = job.slots + static_cast<size_t>(active ? interval : first_line) * slot_bytes;
     assume_global(slot);
-    enc.begin(h, contexts + threadIdx.x, fast_block_threads, slot);
+    enc.begin(h, contexts + threadIdx.x - first_context * fast_block_threads, fast_block_threads, slot);
 
     const uint8_t* pixels = job.pixels_in;
     assume_global(pixels);
@@ -190,6 +219,28 @@ __global__ void __launch_bounds__(fast_block_threads)
             // cadence at once (pixels_per_tile is a multiple of 4: groups end where n is one); both advance on the FMA pipe
             uint32_t sample = static_cast<uint32_t>(__cvta_generic_to_shared(&tiles[warp][t & 1][lane * SW]));
             int32_t n = min(pixels_per_tile, width - t * pixels_per_tile);
+            if (unrolled_groups && (n & drain_mask) == 0)
+            {
+                // Whole groups only (every tile of a line whose width is a multiple of the cadence): the group is written out,
+                // its samples are read at immediate offsets and the two loop registers advance once per group.
+                do
+                {
+                    enc.drain();
+#pragma unroll
+                    for (int32_t g = 0; g <= drain_mask; ++g)
+                    {
+                        int32_t v[NC];
+#pragma unroll
+                        for (int32_t c = 0; c < NC; ++c)
+                            v[c] = load_shared_sample<S>(sample, g * NC + c);
+                        enc.pixel(h, v);
+                    }
+                    sample = static_cast<uint32_t>(
+                        add_fma(h, static_cast<int32_t>(sample), (drain_mask + 1) * NC * static_cast<int32_t>(sizeof(S))));
+                    n = add_fma(h, n, -(drain_mask + 1));
+                } while (n != 0);
+            }
+            else
             do
             {
                 enc.drain(); // every fourth pixel (every pixel_per_drain-th), for all lanes of the warp together
@@ -233,8 +284,10 @@ __global__ void __launch_bounds__(fast_block_threads)
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
     // pixels between two top-ups of the 128-bit read window (see FastReader::get_golomb_steady)
-    constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, lut_none>::pixels_per_top_up;
-    __shared__ RegularContext contexts[5 * fast_block_threads];
+    constexpr int refill_cadence = FastLineDecoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, DEPTH>::pixels_per_top_up;
+    constexpr bool unrolled_groups = JLS_UNROLL_DECODER && NC == 1 && DEPTH != 0 && refill_cadence > 1;
+    constexpr int first_context = NC == 1 ? 1 : 0; // scalar lines never use context 0 (FastLineState::first_context)
+    __shared__ RegularContext contexts[(5 - first_context) * fast_block_threads];
     __shared__ uint32_t tiles[warps][32 * SW];
     extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
@@ -279,13 +332,18 @@ __global__ void __launch_bounds__(fast_block_threads)
     keep_hot_params_in_registers(h, hot_scratch[warp]);
     if (DEPTH != 0)
     {
+        // lossless at full depth: RANGE = 2^DEPTH, qbpp = DEPTH, LIMIT = 2 (DEPTH + max(8, DEPTH)) (make_codec_params)
         h.bits = DEPTH;
         h.maxval = (1 << DEPTH) - 1;
+        h.qbpp = DEPTH;
+        h.limit = 2 * (DEPTH + (DEPTH > 8 ? DEPTH : 8));
+        h.escape = h.limit - DEPTH - 1;
     }
     FastLineDecoder<NC, LOSSLESS, sizeof(S) == 1 ? lut_full : lut_clamped, DEPTH> dec;
     const uint8_t* stream = job.stream_in;
     assume_global(stream);
-    dec.begin(h, contexts + threadIdx.x, fast_block_threads, stream + (coding ? begin : 0), stream + (coding ? end : 0));
+    dec.begin(h, contexts + threadIdx.x - first_context * fast_block_threads, fast_block_threads, stream + (coding ? begin : 0),
+              stream + (coding ? end : 0));
 
     uint8_t* pixels = job.pixels_out;
     assume_global(pixels);
@@ -306,6 +364,26 @@ __global__ void __launch_bounds__(fast_block_threads)
             // the pixels left in the line are needed on the rare run-mode path only
             const int32_t beyond = max(width - x0 - pixels_per_tile, 0); // pixels of the line after this tile
             int32_t n = width - x0 - beyond;
+            if (unrolled_groups && (n & (refill_cadence - 1)) == 0)
+            {
+                constexpr int32_t unroll = refill_cadence < 4 ? refill_cadence : 4; // pixels written out per loop iteration
+                do
+                {
+                    if (unroll == refill_cadence || (n & (refill_cadence - 1)) == 0)
+                        dec.top_up();
+#pragma unroll
+                    for (int32_t g = 0; g < unroll; ++g)
+                    {
+                        dec.pixel(h, beyond, n - g);
+#pragma unroll
+                        for (int32_t c = 0; c < NC; ++c)
+                            store_shared_sample<S>(sample, g * NC + c, dec.ra[c]);
+                    }
+                    sample = static_cast<uint32_t>(add_fma(h, static_cast<int32_t>(sample), unroll * NC * static_cast<int32_t>(sizeof(S))));
+                    n = add_fma(h, n, -unroll);
+                } while (n != 0);
+            }
+            else
             do
             {
                 dec.top_up(); // at the start of every group of refill_cadence pixels

@@ -42,9 +42,11 @@ __device__ __forceinline__ void cp_async_wait()
 template<int TW>
 struct TileWalk
 {
-    static_assert(TW == 16 || TW == 24, "tiles are 64 or 96 bytes wide");
-    static constexpr int period = TW == 16 ? 1 : 3;
-    static constexpr int rows = TW == 16 ? 2 : 4;
+    static_assert(TW == 8 || TW == 12 || TW == 16 || TW == 24, "tiles are 32, 48, 64 or 96 bytes wide");
+    // 32 words per step: four 32-byte rows or two 64-byte rows; 48- and 96-byte rows repeat after three steps (96 words =
+    // eight / four rows)
+    static constexpr int period = (TW == 24 || TW == 12) ? 3 : 1;
+    static constexpr int rows = TW == 16 ? 2 : TW == 12 ? 8 : 4;
     static constexpr int groups = 32 / rows;
     uint32_t global_offset[period]; // bytes from the group's first row in global memory
     uint32_t shared_offset[period]; // bytes from the group's first row in the padded shared-memory tile
