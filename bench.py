@@ -62,6 +62,9 @@ def parse_args():
     ap.add_argument("--restart-interval", type=int, default=1,
                     help="lines per restart interval; 1 = every line an independent work item (the design point), 0 = none: the "
                          "streams the reference itself writes, one CUDA thread per scan (the general path)")
+    ap.add_argument("--no-offset-table", action="store_true",
+                    help="batch streams without the side table of interval offsets (APP11 \"JLS-OFFT\", include/charls_b200.h): the "
+                         "decoder then searches every stream for its restart markers (three more kernels)")
     ap.add_argument("--content", default="smooth", choices=["smooth", "noise", "flat"],
                     help="smooth = S_smooth (the metric's input); noise (uniform, incompressible) and flat (all zero, pure run "
                          "mode) bracket it (SURVEY.md 8d)")
@@ -393,14 +396,15 @@ def e2e_round_trip(lib, frames_host, streams_host, out_host, workload, threads, 
     return time.perf_counter() - t0, sizes
 
 
-def secondary_workload(torch, dist, lib, device, rank, world, workload, F, steps, peak):
+def secondary_workload(torch, dist, lib, device, rank, world, workload, F, steps, peak, offset_table=True):
     """The metric names two inputs (8-bit mono and 16-bit RGB): the other one, measured like `value` (device-resident frames,
     CUDA events on the coder stream, max over ranks) with fewer frames and steps, reported under "also"."""
     from charls_b200.batch import BatchCodec
 
     w, h, bits, cc, near, ilv, xf = WORKLOADS[workload]
     frames = make_frames(torch, device, F, workload, first_seed=1234 + rank * F)
-    codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=1, lib=lib)
+    codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, restart_interval=1,
+                       offset_table=offset_table, lib=lib)
     streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
     decoded = torch.empty_like(frames)
     raw_bytes = frames[0].numel() * frames.element_size()
@@ -466,7 +470,7 @@ def run_gpu_arm(args):
     F = args.frames
     frames = make_frames(torch, device, F, args.workload, first_seed=1234 + rank * F, content=args.content)
     codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf,
-                       restart_interval=args.restart_interval, lib=lib)
+                       restart_interval=args.restart_interval, offset_table=not args.no_offset_table, lib=lib)
     if args.content == "noise":
         codec.stream_capacity *= 2  # incompressible input expands (about 9.5 bits per 8-bit sample)
     streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
@@ -660,7 +664,8 @@ def run_gpu_arm(args):
         del frames, streams, decoded
         torch.cuda.empty_cache()
         for other in others:
-            also[other] = secondary_workload(torch, dist, lib, device, rank, world, other, max(1, args.frames // 2), max(3, args.steps // 4), peak)
+            also[other] = secondary_workload(torch, dist, lib, device, rank, world, other, max(1, args.frames // 2), max(3, args.steps // 4), peak,
+                                             not args.no_offset_table)
 
     if rank != 0:
         if world > 1:
@@ -729,6 +734,7 @@ def run_gpu_arm(args):
                    "compressed_bytes_per_frame": comp_per_frame, "ratio": raw_bytes / comp_per_frame,
                    "cache": f"inputs larger than L2: {F * raw_bytes / 1e6:.0f} MB raw + {F * comp_per_frame / 1e6:.0f} MB streams per GPU vs 126 MB L2",
                    "sharding": "frames split across ranks, no data-path collective; NCCL all_gather of stream sizes only",
+                   "offset_table": not args.no_offset_table and args.restart_interval != 0,
                    **config_also},
         "encode_mpix_s": world * F * w * h / (t_enc * 1e-3) / 1e6, "decode_mpix_s": world * F * w * h / (t_dec * 1e-3) / 1e6,
         "roofline": dominant, "roofline_all": roofs, "cpu_baseline": cpu_baseline, "e2e": e2e, "also": also or None, "clocks": clocks,

@@ -14,11 +14,13 @@ class BatchCodec:
     """Encodes / decodes batches of equally shaped frames that live in CUDA tensors."""
 
     def __init__(self, width, height, bits_per_sample, component_count=1, *, near_lossless=0, interleave_mode=0,
-                 color_transformation=0, restart_interval=1, lib: CharlsLibrary | None = None):
+                 color_transformation=0, restart_interval=1, offset_table=False, lib: CharlsLibrary | None = None):
+        """offset_table: write (encode) / look for (decode) the side table of interval offsets in the streams' headers
+        (CHARLSX_BATCH_OFFSET_TABLE, include/charls_b200.h)."""
         self.lib = lib or default_library()
         self.params = BatchParams(
             FrameInfo(width, height, bits_per_sample, component_count), near_lossless, interleave_mode, color_transformation,
-            restart_interval, 0, 0,
+            restart_interval, 0, 1 if offset_table and restart_interval else 0,
         )
         self._h = self.lib.charlsx_batch_create()
         if not self._h:
@@ -28,6 +30,8 @@ class BatchCodec:
         # same bound the single-image encoder reports (reference formula + restart-marker overhead)
         intervals = (height + restart_interval - 1) // restart_interval if restart_interval else 0
         self.stream_capacity = self.frame_bytes + self.frame_bytes // 16 + 1024 + 34 + 4 * intervals + 8
+        if offset_table and restart_interval:
+            self.stream_capacity += 4 * (intervals + 1) + 26 * ((intervals + 1) // 16377 + 1)
         self.stream_capacity = (self.stream_capacity + 255) // 256 * 256
 
     def close(self):
@@ -70,6 +74,16 @@ class BatchCodec:
         errc = self.lib.charlsx_batch_decode(self._h, byref(self.params), images, len(images), self._stream_handle(stream))
         self.lib.check(errc)
         return [images[i].stream_size for i in range(len(images))]
+
+    def decode_new(self, streams, sizes, stream=None):
+        """decode() into a new CUDA tensor [N, H, W] or [N, H, W, C] (uint8, or int16 carrying the uint16 bit pattern)."""
+        import torch
+
+        fi = self.params.frame_info
+        shape = (streams.shape[0], fi.height, fi.width) + ((fi.component_count,) if fi.component_count > 1 else ())
+        out = torch.empty(shape, dtype=torch.uint8 if fi.bits_per_sample <= 8 else torch.int16, device=streams.device)
+        self.decode(streams, sizes, out, stream)
+        return out
 
     # ---- frames and streams in host memory (numpy arrays or pinned torch tensors); see charlsx_batch_encode_host
     @staticmethod

@@ -143,7 +143,7 @@ class BatchParams(C.Structure):
         ("color_transformation", c_int32),
         ("restart_interval", c_uint32),
         ("stride", c_uint32),
-        ("reserved", c_uint32),
+        ("flags", c_uint32),
     ]
 
 
@@ -153,6 +153,7 @@ EXT_SYMBOLS = {
     "charlsx_set_device": (_ERR, [c_int32]),
     "charlsx_jpegls_encoder_set_restart_interval": (_ERR, [_E, c_uint32]),
     "charlsx_jpegls_decoder_get_restart_interval": (_ERR, [_D, POINTER(c_uint32)]),
+    "charlsx_jpegls_encoder_set_offset_table": (_ERR, [_E, c_int32]),
     "charlsx_jpegls_encoder_encode_from_buffer_begin": (_ERR, [_E, c_void_p, c_size_t, c_uint32]),
     "charlsx_jpegls_encoder_encode_end": (_ERR, [_E]),
     "charlsx_jpegls_decoder_decode_to_buffer_begin": (_ERR, [_D, c_void_p, c_size_t, c_uint32]),

@@ -78,6 +78,11 @@ class JpegLSEncoder:
         self.lib.check(self.lib.charls_jpegls_encoder_set_preset_coding_parameters(self._h, byref(pc)))
         return self
 
+    def offset_table(self, enabled=True):
+        """Side table of interval offsets in front of every scan (extension, include/charls_b200.h)."""
+        self.lib.check(self.lib.charlsx_jpegls_encoder_set_offset_table(self._h, 1 if enabled else 0))
+        return self
+
     def restart_interval(self, lines):
         """B200 extension (charlsx_jpegls_encoder_set_restart_interval); the reference cannot encode restart markers."""
         self.lib.check(self.lib.charlsx_jpegls_encoder_set_restart_interval(self._h, lines))

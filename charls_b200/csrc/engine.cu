@@ -511,16 +511,16 @@ int32_t Engine::fetch_outcomes(size_t job_count, CUstream_st* stream)
 // C ABI path: host buffers
 // ---------------------------------------------------------------------------------------------------------------------
 int32_t Engine::encode_scan_from_host(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
-                                      size_t capacity, size_t& written)
+                                      size_t capacity, size_t& written, const HostOffsetTable* table)
 {
     written = 0;
-    JLS_CHECK(encode_scan_from_host_begin(p, source, stride, destination, capacity));
+    JLS_CHECK(encode_scan_from_host_begin(p, source, stride, destination, capacity, table));
     return encode_scan_from_host_end(written);
 }
 
 // Everything of an encode that needs no answer from the device: input copy, kernels, the 32-byte outcome.  Nothing waits.
 int32_t Engine::encode_scan_from_host_begin(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
-                                            size_t capacity)
+                                            size_t capacity, const HostOffsetTable* table)
 {
     pending_ = Pending{};
     JLS_CHECK(prepare());
@@ -557,15 +557,27 @@ int32_t Engine::encode_scan_from_host_begin(const CodecParams& p, const uint8_t*
     jobs[0].stride = pitch;
     jobs[0].stream_out = direct ? direct : static_cast<uint8_t*>(stream_buffer_.data);
     jobs[0].stream_out_capacity = device_capacity;
+    // side table of interval offsets: the entries are made on the device (big endian, segment after segment in
+    // table_buffer_) and copied into the places the header reserves for them once the scan is done
+    const bool with_table = table != nullptr && table->total == p.interval_count + 1U;
+    if (with_table)
+    {
+        JLS_CHECK(ensure(table_buffer_, static_cast<size_t>(table->total) * 4U + 64));
+        jobs[0].offset_table.total = table->total;
+        for (uint32_t segment = 0; segment < offset_table_segment_count(table->total); ++segment)
+            jobs[0].offset_table.entries[segment] =
+                static_cast<uint8_t*>(table_buffer_.data) + static_cast<size_t>(segment) * offset_table_entries_per_segment * 4U;
+    }
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream_, false));
     JLS_CHECK(ensure(host_outcomes_, outcome_words * sizeof(uint64_t), true));
     GraphKey key{};
     key.p = p;
     key.slot_bytes = slot_bytes;
     key.encode = 1;
+    key.reserved = with_table ? 1U : 0U;
     JLS_CHECK(replay(key, [&]() -> int32_t {
         JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, sizeof(ScanJob), cudaMemcpyHostToDevice, stream_));
-        JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, nullptr, true));
+        JLS_CUDA(launch_encode(p, static_cast<const ScanJob*>(job_table_.data), 1, slot_bytes, stream_, nullptr, true, with_table));
         JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                  stream_));
         return 0;
@@ -576,6 +588,8 @@ int32_t Engine::encode_scan_from_host_begin(const CodecParams& p, const uint8_t*
     pending_.destination = destination;
     pending_.capacity = capacity;
     pending_.direct = direct != nullptr;
+    if (with_table)
+        pending_.host_table = *table;
     return 0;
 }
 
@@ -597,9 +611,18 @@ int32_t Engine::encode_scan_from_host_end(size_t& written)
     const uint64_t total = outcome[1];
     if (total > pending_.capacity)
         return err_destination_too_small;
-    if (total != 0 && !pending_.direct)
+    const uint32_t table_entries = pending_.host_table.total;
+    for (uint32_t segment = 0; segment < offset_table_segment_count(table_entries) && table_entries != 0; ++segment)
     {
-        JLS_CUDA(cudaMemcpyAsync(pending_.destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
+        const uint32_t first = segment * offset_table_entries_per_segment;
+        const uint32_t count = table_entries - first < offset_table_entries_per_segment ? table_entries - first : offset_table_entries_per_segment;
+        JLS_CUDA(cudaMemcpyAsync(pending_.host_table.entries[segment], static_cast<const uint8_t*>(table_buffer_.data) + static_cast<size_t>(first) * 4U,
+                                 static_cast<size_t>(count) * 4U, cudaMemcpyDeviceToHost, stream_));
+    }
+    if ((total != 0 && !pending_.direct) || table_entries != 0)
+    {
+        if (total != 0 && !pending_.direct)
+            JLS_CUDA(cudaMemcpyAsync(pending_.destination, stream_buffer_.data, total, cudaMemcpyDeviceToHost, stream_));
         trace_gpu(3);
         JLS_CHECK(wait_for(stream_));
     }
@@ -621,15 +644,17 @@ int32_t Engine::upload_stream(const uint8_t* host_stream, size_t size)
     return 0;
 }
 
-int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed)
+int32_t Engine::decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed,
+                                    const StreamOffsetTable* table)
 {
     consumed = 0;
-    JLS_CHECK(decode_scan_to_host_begin(p, offset, destination, stride));
+    JLS_CHECK(decode_scan_to_host_begin(p, offset, destination, stride, table));
     return decode_scan_to_host_end(consumed);
 }
 
 // Kernels, outcome and the copy of the samples to the caller's buffer are all issued here; nothing waits.
-int32_t Engine::decode_scan_to_host_begin(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride)
+int32_t Engine::decode_scan_to_host_begin(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride,
+                                          const StreamOffsetTable* table)
 {
     pending_ = Pending{};
     JLS_CHECK(prepare());
@@ -655,16 +680,26 @@ int32_t Engine::decode_scan_to_host_begin(const CodecParams& p, size_t offset, u
     jobs[0].stride = pitch;
     jobs[0].stream_in = static_cast<const uint8_t*>(stream_buffer_.data) + offset;
     jobs[0].stream_in_size = remaining;
+    // a side table of interval offsets in the stream's header replaces the marker search (it is checked on the device; if
+    // the stream does not agree with it, decode_scan_to_host_end decodes again without)
+    const bool with_table = table != nullptr && table->total == p.interval_count + 1U;
+    if (with_table)
+    {
+        jobs[0].offset_table.total = table->total;
+        for (uint32_t segment = 0; segment < offset_table_segment_count(table->total); ++segment)
+            jobs[0].offset_table.entries[segment] = static_cast<uint8_t*>(stream_buffer_.data) + table->entry_offsets[segment];
+    }
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream_, false));
     JLS_CHECK(ensure(host_outcomes_, outcome_words * sizeof(uint64_t), true));
     GraphKey key{};
     key.p = p;
     key.marker_blocks = blocks;
+    key.reserved = with_table ? 1U : 0U;
     JLS_CHECK(replay(key, [&]() -> int32_t {
         JLS_CUDA(cudaMemcpyAsync(job_table_.data, host_jobs_.data, sizeof(ScanJob), cudaMemcpyHostToDevice, stream_));
         JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), 1, grid_bytes,
                                static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                               static_cast<uint8_t*>(marker_codes_.data), stream_, nullptr, true));
+                               static_cast<uint8_t*>(marker_codes_.data), stream_, nullptr, true, with_table));
         JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                                  stream_));
         return 0;
@@ -682,6 +717,11 @@ int32_t Engine::decode_scan_to_host_begin(const CodecParams& p, size_t offset, u
     trace_gpu(3);
     trace_host(1);
     pending_.active = true;
+    pending_.used_table = with_table;
+    pending_.p = p;
+    pending_.offset = offset;
+    pending_.destination = destination;
+    pending_.stride = stride;
     return 0;
 }
 
@@ -692,6 +732,14 @@ int32_t Engine::decode_scan_to_host_end(size_t& consumed)
         return 100; // invalid_operation
     pending_.active = false;
     JLS_CHECK(wait_for(stream_));
+    if (pending_.used_table && static_cast<const uint64_t*>(host_outcomes_.data)[0] != ~0ULL)
+    {
+        // Not a clean decode with the side table: the table may be wrong, or the stream damaged.  Either way the answer is
+        // what the marker search gives (errors included), so decode once more without the table.
+        const Pending again = pending_;
+        JLS_CHECK(decode_scan_to_host_begin(again.p, again.offset, again.destination, again.stride, nullptr));
+        return decode_scan_to_host_end(consumed);
+    }
     trace_host(2);
     last_coder_ms_ = 0.0F; // not measured on this path (the batch interface does)
     last_launches_ = static_cast<uint32_t>(thread_kernel_launch_count() - pending_.launches_before);
@@ -709,11 +757,12 @@ int32_t Engine::decode_scan_to_host_end(size_t& consumed)
 // Batch path: device-resident frames
 // ---------------------------------------------------------------------------------------------------------------------
 int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
-                             size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding)
+                             size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding,
+                             const StreamOffsetTable* table)
 {
     if (count == 0)
         return prepare();
-    JLS_CHECK(encode_batch_begin(p, header, header_size, frames, count, stride, user_stream));
+    JLS_CHECK(encode_batch_begin(p, header, header_size, frames, count, stride, user_stream, table));
     if (while_coding)
         JLS_CHECK(while_coding());
     return encode_batch_end(frames, count, header_size, user_stream);
@@ -722,7 +771,7 @@ int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t
 // Issues the whole batch (job table, kernels, headers and EOI, outcome copy) on `user_stream` or the engine's own stream
 // and returns; encode_batch_end waits and fills in sizes and statuses.
 int32_t Engine::encode_batch_begin(const CodecParams& p, const uint8_t* header, size_t header_size, const BatchFrame* frames,
-                                   size_t count, size_t stride, CUstream_st* user_stream)
+                                   size_t count, size_t stride, CUstream_st* user_stream, const StreamOffsetTable* table)
 {
     JLS_CHECK(prepare());
     cudaStream_t stream = user_stream ? user_stream : stream_;
@@ -736,6 +785,7 @@ int32_t Engine::encode_batch_begin(const CodecParams& p, const uint8_t* header, 
     std::memcpy(host_prefixes_.data, header, header_size);
     JLS_CUDA(cudaMemcpyAsync(header_.data, host_prefixes_.data, header_size, cudaMemcpyHostToDevice, stream));
 
+    const bool with_table = table != nullptr && table->total == p.interval_count + 1U;
     // the tile kernels keep row offsets of up to three strides in 32 bits (jls_tile.cuh, TileWalk)
     bool word_aligned = stride % 4 == 0 && stride < (size_t{1} << 30);
     std::vector<ScanJob> jobs(count);
@@ -749,12 +799,22 @@ int32_t Engine::encode_batch_begin(const CodecParams& p, const uint8_t* header, 
         const bool room = frames[i].stream_capacity >= header_size + 2;
         job.stream_out = frames[i].stream + header_size;
         job.stream_out_capacity = room ? frames[i].stream_capacity - header_size - 2 : 0;
+        if (with_table && room)
+        {
+            job.offset_table.total = table->total;
+            for (uint32_t segment = 0; segment < offset_table_segment_count(table->total); ++segment)
+                job.offset_table.entries[segment] = frames[i].stream + table->entry_offsets[segment];
+        }
     }
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream));
     const ScanJob* device_jobs = static_cast<const ScanJob*>(job_table_.data);
-    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream, events_, word_aligned));
+    // the header (with the table's entries still zero) goes in first, the entries are written over it
+    if (with_table)
+        JLS_CUDA(launch_wrap_frames(device_jobs, static_cast<const uint8_t*>(header_.data), static_cast<uint32_t>(header_size),
+                                    static_cast<uint32_t>(count), stream, wrap_header));
+    JLS_CUDA(launch_encode(p, device_jobs, static_cast<uint32_t>(count), slot_bytes, stream, events_, word_aligned, with_table));
     JLS_CUDA(launch_wrap_frames(device_jobs, static_cast<const uint8_t*>(header_.data), static_cast<uint32_t>(header_size),
-                                static_cast<uint32_t>(count), stream));
+                                static_cast<uint32_t>(count), stream, with_table ? wrap_end_of_image : wrap_header | wrap_end_of_image));
     JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
     JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                              stream));
@@ -838,7 +898,7 @@ size_t Engine::staging_chunk(size_t count, size_t bytes_per_frame) noexcept
 }
 
 int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
-                                  size_t stride)
+                                  size_t stride, const StreamOffsetTable* table)
 {
     if (count == 0)
         return 0;
@@ -888,7 +948,7 @@ int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, s
         }
         Engine& engine = engine_of(j);
         JLS_CUDA(cudaStreamWaitEvent(engine.stream_, in_done_[s], 0));
-        return engine.encode_batch_begin(p, header, header_size, staged[s].data(), n, stride, engine.stream_);
+        return engine.encode_batch_begin(p, header, header_size, staged[s].data(), n, stride, engine.stream_, table);
     };
     int32_t first_error = 0;
     uint32_t launches = 0;
@@ -939,6 +999,7 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
     if (count == 0)
         return 0;
     JLS_CHECK(prepare_staging());
+    bool with_tables[staging_slots] = {};
     const size_t row_bytes = row_bytes_of(p);
     const size_t frame_bytes = stride * (static_cast<size_t>(p.height) - 1) + row_bytes;
     const size_t frame_pitch = align_up(stride * static_cast<size_t>(p.height), 256);
@@ -976,10 +1037,11 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
         for (size_t k = 0; k < n; ++k)
             staged[s][k] = BatchFrame{static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch,
                                       static_cast<uint8_t*>(stage_streams_[s].data) + k * stream_slot, frames[first + k].stream_capacity, 0, 0,
-                                      frames[first + k].scan_offset};
+                                      frames[first + k].scan_offset, frames[first + k].table};
         Engine& engine = engine_of(j);
         JLS_CUDA(cudaStreamWaitEvent(engine.stream_, in_done_[s], 0));
-        return engine.decode_batch_begin(p, staged[s].data(), n, stride, engine.stream_);
+        with_tables[s] = all_frames_have_tables(p, staged[s].data(), n);
+        return engine.decode_batch_begin(p, staged[s].data(), n, stride, engine.stream_, with_tables[s]);
     };
     int32_t first_error = 0;
     uint32_t launches = 0;
@@ -988,7 +1050,13 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
         const int s = static_cast<int>(j % staging_slots);
         const size_t first = j * chunk, n = frames_in(j);
         Engine& engine = engine_of(j);
-        const int32_t status = engine.decode_batch_end(staged[s].data(), n, engine.stream_);
+        int32_t status = engine.decode_batch_end(staged[s].data(), n, engine.stream_);
+        if (status != 0 && with_tables[s])
+        {
+            // not a clean decode with the side tables: once more by marker search (decode_scan_to_host_end)
+            JLS_CHECK(engine.decode_batch_begin(p, staged[s].data(), n, stride, engine.stream_, false));
+            status = engine.decode_batch_end(staged[s].data(), n, engine.stream_);
+        }
         launches += engine.last_launches_;
         coder_ms += engine.last_coder_ms_;
         if (status != 0 && first_error == 0)
@@ -1057,14 +1125,34 @@ int32_t Engine::decode_batch(const CodecParams& p, BatchFrame* frames, size_t co
 {
     if (count == 0)
         return prepare();
-    JLS_CHECK(decode_batch_begin(p, frames, count, stride, user_stream));
+    const bool use_tables = all_frames_have_tables(p, frames, count);
+    JLS_CHECK(decode_batch_begin(p, frames, count, stride, user_stream, use_tables));
     if (while_coding)
         JLS_CHECK(while_coding());
+    const int32_t status = decode_batch_end(frames, count, user_stream);
+    if (status == 0 || !use_tables)
+        return status;
+    // not a clean decode with the side tables: the answer is what the marker search gives (decode_scan_to_host_end)
+    JLS_CHECK(decode_batch_begin(p, frames, count, stride, user_stream, false));
     return decode_batch_end(frames, count, user_stream);
 }
 
+bool Engine::all_frames_have_tables(const CodecParams& p, const BatchFrame* frames, size_t count) noexcept
+{
+    static const bool disabled = [] {
+        const char* value = std::getenv("CHARLS_B200_IGNORE_OFFSET_TABLES");
+        return value && value[0] == '1';
+    }();
+    if (disabled)
+        return false;
+    for (size_t i = 0; i < count; ++i)
+        if (frames[i].table.total != p.interval_count + 1U)
+            return false;
+    return count != 0;
+}
+
 int32_t Engine::decode_batch_begin(const CodecParams& p, const BatchFrame* frames, size_t count, size_t stride,
-                                   CUstream_st* user_stream)
+                                   CUstream_st* user_stream, bool use_tables)
 {
     JLS_CHECK(prepare());
     cudaStream_t stream = user_stream ? user_stream : stream_;
@@ -1084,6 +1172,12 @@ int32_t Engine::decode_batch_begin(const CodecParams& p, const BatchFrame* frame
         job.stream_in = frames[i].stream + frames[i].scan_offset;
         job.stream_in_size = frames[i].stream_capacity - frames[i].scan_offset;
         max_remaining = job.stream_in_size > max_remaining ? job.stream_in_size : max_remaining;
+        if (use_tables)
+        {
+            job.offset_table.total = frames[i].table.total;
+            for (uint32_t segment = 0; segment < offset_table_segment_count(frames[i].table.total); ++segment)
+                job.offset_table.entries[segment] = frames[i].stream + frames[i].table.entry_offsets[segment];
+        }
     }
     JLS_CHECK(ensure(marker_counts_, marker_scratch_bytes(count, max_remaining)));
     JLS_CHECK(ensure(marker_totals_, count * sizeof(uint32_t)));
@@ -1091,7 +1185,7 @@ int32_t Engine::decode_batch_begin(const CodecParams& p, const BatchFrame* frame
     JLS_CHECK(stage_jobs(p, jobs, false, 0, stream));
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), static_cast<uint32_t>(count), max_remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
-                           static_cast<uint8_t*>(marker_codes_.data), stream, events_, word_aligned));
+                           static_cast<uint8_t*>(marker_codes_.data), stream, events_, word_aligned, use_tables));
     JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
     JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                              stream));

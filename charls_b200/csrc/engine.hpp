@@ -28,6 +28,18 @@ constexpr int32_t errc_not_enough_memory = 1;
 int32_t set_device(int32_t ordinal) noexcept; // process-wide device used by every engine
 int32_t device_count(int32_t* count) noexcept;
 
+// Where the entries of a side table of interval offsets (jls_common.h) are, segment by segment; total = 0: no table.
+struct HostOffsetTable // single-image encode: absolute host addresses inside the destination's header
+{
+    uint32_t total{};
+    uint8_t* entries[offset_table_max_segments]{};
+};
+struct StreamOffsetTable // offsets from the first byte of a stream (the same for every frame of a batch encode)
+{
+    uint32_t total{};
+    size_t entry_offsets[offset_table_max_segments]{};
+};
+
 struct BatchFrame
 {
     uint8_t* pixels;        // device
@@ -37,6 +49,7 @@ struct BatchFrame
     int32_t status;         // out
     // decode only, filled by the caller after parsing the header on the host:
     size_t scan_offset; // offset of the first entropy-coded byte
+    StreamOffsetTable table{}; // the frame's side table of interval offsets, if its header has one
 };
 
 class Engine final
@@ -50,35 +63,40 @@ public:
     // Encodes one scan whose samples are in host memory at `source` (line pitch `stride`) and writes the entropy-coded
     // data (interval data + RSTm markers) to host memory at `destination`.  Returns a charls_jpegls_errc.
     int32_t encode_scan_from_host(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
-                                  size_t capacity, size_t& written);
+                                  size_t capacity, size_t& written, const HostOffsetTable* table = nullptr);
 
     // The same call in two halves (charlsx_*_begin / _end): `begin` issues the input copy, the kernels and the outcome copy
     // and returns without waiting, `end` waits and moves the entropy-coded bytes.  One pending half per engine; a host
     // thread keeps several codec objects (= engines = CUDA streams) in flight this way.
     int32_t encode_scan_from_host_begin(const CodecParams& p, const uint8_t* source, size_t stride, uint8_t* destination,
-                                        size_t capacity);
+                                        size_t capacity, const HostOffsetTable* table = nullptr);
     int32_t encode_scan_from_host_end(size_t& written);
-    int32_t decode_scan_to_host_begin(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride);
+    int32_t decode_scan_to_host_begin(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride,
+                                      const StreamOffsetTable* table = nullptr);
     int32_t decode_scan_to_host_end(size_t& consumed);
 
     // Copies a complete JPEG-LS stream to the device once; decode_scan_to_host then works on offsets into it.
     int32_t upload_stream(const uint8_t* host_stream, size_t size);
     // Decodes the scan whose entropy-coded data starts `offset` bytes into the uploaded stream.
     // `consumed` = bytes of entropy-coded data (up to the marker that ends the scan).
-    int32_t decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed);
+    int32_t decode_scan_to_host(const CodecParams& p, size_t offset, uint8_t* destination, size_t stride, size_t& consumed,
+                                const StreamOffsetTable* table = nullptr);
 
     // Device-resident batches (single-scan frames).  `header` = the bytes in front of the entropy-coded data.
     // `while_coding` (optional) runs on the host after all work of the call has been issued and before the call waits
     // for it: the host-resident path issues the next chunk's copies there, behind this chunk's kernels.
+    // `table` (encode): where the header reserves the side table of interval offsets, relative to every frame's stream.
+    // Decode: frames[i].table; the tables are used when every frame of the batch has one.
     int32_t encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
-                         size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding = {});
+                         size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding = {},
+                         const StreamOffsetTable* table = nullptr);
     int32_t decode_batch(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream,
                          const std::function<int32_t()>& while_coding = {});
     // The same for frames and streams in HOST memory (pinned for full speed): the engine stages a chunk of frames at a
     // time in device memory and overlaps the copies of one chunk with the kernels of its neighbours (three CUDA
     // streams, double-buffered staging).  BatchFrame pointers are host pointers here.
     int32_t encode_batch_host(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
-                              size_t stride);
+                              size_t stride, const StreamOffsetTable* table = nullptr);
     int32_t decode_batch_host(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride);
     // Downloads the first `prefix_bytes` of every frame's stream (header parsing happens on the host).
     int32_t download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, std::vector<uint8_t>& prefixes,
@@ -142,11 +160,17 @@ private:
         uint8_t* destination{};
         size_t capacity{};
         uint64_t launches_before{};
+        // encode: where the side table goes on the host; decode: what a second attempt without the table needs
+        HostOffsetTable host_table{};
+        bool used_table{};
+        CodecParams p{};
+        size_t offset{};
+        size_t stride{};
     };
     Pending pending_;
     CUstream_st* stream_{};
     int device_{-1};
-    Buffer pixels_, stream_buffer_, slots_, interval_bytes_, interval_offset_, line_scratch_, job_table_, outcomes_,
+    Buffer pixels_, stream_buffer_, slots_, interval_bytes_, interval_offset_, line_scratch_, job_table_, outcomes_, table_buffer_,
         marker_counts_, marker_totals_, marker_codes_, header_, pointer_table_, prefixes_;
     Buffer host_outcomes_, host_jobs_, host_prefixes_, host_pointer_table_; // pinned
     size_t uploaded_stream_size_{};
@@ -168,9 +192,11 @@ private:
     uint64_t batch_launches_before_{};
     // the two halves of encode_batch / decode_batch: issue everything, then wait and collect sizes / statuses
     int32_t encode_batch_begin(const CodecParams& p, const uint8_t* header, size_t header_size, const BatchFrame* frames, size_t count,
-                               size_t stride, CUstream_st* user_stream);
+                               size_t stride, CUstream_st* user_stream, const StreamOffsetTable* table = nullptr);
     int32_t encode_batch_end(BatchFrame* frames, size_t count, size_t header_size, CUstream_st* user_stream);
-    int32_t decode_batch_begin(const CodecParams& p, const BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream);
+    int32_t decode_batch_begin(const CodecParams& p, const BatchFrame* frames, size_t count, size_t stride, CUstream_st* user_stream,
+                               bool use_tables);
+    static bool all_frames_have_tables(const CodecParams& p, const BatchFrame* frames, size_t count) noexcept;
     int32_t decode_batch_end(BatchFrame* frames, size_t count, CUstream_st* user_stream);
     // CHARLS_B200_TRACE timeline of the single-image calls (engine.cu: Trace)
     void trace_gpu(int index) noexcept;

@@ -83,10 +83,15 @@ charls_jpegls_errc encode_frames(charlsx_batch* batch, const charlsx_batch_param
         const size_t stride = effective_stride(bp);
         const charls_frame_info& f = bp.frame_info;
 
-        // the header every frame gets: SOI [APP8 mrfx] SOF55 [DRI] SOS -- what the single-image encoder writes
-        uint8_t header[128];
+        // the header every frame gets: SOI [APP8 mrfx] SOF55 [DRI] [APP11 side table of interval offsets] SOS -- what the
+        // single-image encoder writes
+        const bool with_table = (bp.flags & CHARLSX_BATCH_OFFSET_TABLE) != 0 && bp.restart_interval != 0;
+        const uint32_t lines_per_interval = bp.restart_interval != 0 && bp.restart_interval < f.height ? bp.restart_interval : f.height;
+        const uint32_t intervals = (f.height + lines_per_interval - 1) / lines_per_interval;
+        std::vector<uint8_t> header_bytes(128 + (with_table ? offset_table_bytes(intervals) : 0));
+        uint8_t* const header = header_bytes.data();
         StreamWriter writer;
-        writer.destination(header, sizeof(header));
+        writer.destination(header, header_bytes.size());
         writer.write_start_of_image();
         if (bp.color_transformation != 0)
             writer.write_color_transform(bp.color_transformation);
@@ -94,6 +99,12 @@ charls_jpegls_errc encode_frames(charlsx_batch* batch, const charlsx_batch_param
             writer.write_oversize_dimensions(f.height, f.width);
         if (bp.restart_interval != 0)
             writer.write_define_restart_interval(bp.restart_interval);
+        StreamOffsetTable table{};
+        if (with_table)
+        {
+            writer.write_offset_table_placeholder(intervals, table.entry_offsets);
+            table.total = intervals + 1;
+        }
         writer.write_start_of_scan(f.component_count, bp.near_lossless, bp.interleave_mode);
 
         const PresetCodingParameters preset = default_preset_parameters(maximum_bit_sample_value(f.bits_per_sample), bp.near_lossless);
@@ -108,9 +119,10 @@ charls_jpegls_errc encode_frames(charlsx_batch* batch, const charlsx_batch_param
                                           images[i].stream_capacity, 0, 0, 0};
         }
         const int32_t status =
-            host_memory ? batch->engine.encode_batch_host(p, header, writer.bytes_written(), batch->frames.data(), count, stride)
+            host_memory ? batch->engine.encode_batch_host(p, header, writer.bytes_written(), batch->frames.data(), count, stride,
+                                                          table.total != 0 ? &table : nullptr)
                         : batch->engine.encode_batch(p, header, writer.bytes_written(), batch->frames.data(), count, stride,
-                                                     static_cast<CUstream_st*>(cuda_stream));
+                                                     static_cast<CUstream_st*>(cuda_stream), {}, table.total != 0 ? &table : nullptr);
         for (size_t i = 0; i < count; ++i)
         {
             images[i].stream_size = batch->frames[i].stream_size;
@@ -164,9 +176,12 @@ charls_jpegls_errc decode_frames(charlsx_batch* batch, const charlsx_batch_param
 
         // headers are parsed on the host: one gather kernel + one copy brings the first bytes of every stream over
         // (streams in host memory are read where they are)
+        // with side tables of interval offsets in the headers, SOS sits behind them: read that much more of every stream
+        const uint32_t prefix_bytes =
+            header_prefix_bytes + ((bp.flags & CHARLSX_BATCH_OFFSET_TABLE) != 0 ? static_cast<uint32_t>(offset_table_bytes(f.height)) : 0U);
         std::vector<uint8_t> prefixes;
         if (!host_memory)
-            check_status(batch->engine.download_prefixes(batch->frames.data(), count, header_prefix_bytes, prefixes, stream));
+            check_status(batch->engine.download_prefixes(batch->frames.data(), count, prefix_bytes, prefixes, stream));
 
         bool have_params = false;
         CodecParams p{};
@@ -175,10 +190,10 @@ charls_jpegls_errc decode_frames(charlsx_batch* batch, const charlsx_batch_param
         for (size_t i = 0; i < count; ++i)
         {
             BatchFrame& frame = batch->frames[i];
-            const size_t available = frame.stream_capacity < header_prefix_bytes ? frame.stream_capacity : header_prefix_bytes;
+            const size_t available = frame.stream_capacity < prefix_bytes ? frame.stream_capacity : prefix_bytes;
             const charls_jpegls_errc errc = guarded([&] {
                 StreamReader reader;
-                reader.source(host_memory ? frame.stream : prefixes.data() + i * header_prefix_bytes, available);
+                reader.source(host_memory ? frame.stream : prefixes.data() + i * prefix_bytes, available);
                 reader.read_header();
                 const charls_frame_info& info = reader.frame_info();
                 // every frame must match the batch description
@@ -203,6 +218,13 @@ charls_jpegls_errc decode_frames(charlsx_batch* batch, const charlsx_batch_param
                     fail(CHARLS_JPEGLS_ERRC_INVALID_ARGUMENT); // not a uniform batch
                 }
                 frame.scan_offset = reader.position();
+                frame.table = StreamOffsetTable{};
+                if (reader.scan_offset_table().total == q.interval_count + 1U)
+                {
+                    frame.table.total = reader.scan_offset_table().total;
+                    for (uint32_t segment = 0; segment < offset_table_max_segments; ++segment)
+                        frame.table.entry_offsets[segment] = reader.scan_offset_table().entry_offsets[segment];
+                }
             });
             frame.status = errc;
             if (errc == 0)

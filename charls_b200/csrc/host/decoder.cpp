@@ -7,6 +7,8 @@
 #include "abi_support.hpp"
 #include "stream_reader.hpp"
 
+#include <cstdlib>
+
 using namespace jls;
 using namespace jls::host;
 
@@ -144,14 +146,27 @@ struct charls_jpegls_decoder final
                                                     info.bits_per_sample, static_cast<int32_t>(reader_.scan_component_count()),
                                                     reader_.scan_near_lossless(), ilv, ilv != 0 ? reader_.color_transformation() : 0,
                                                     preset, reader_.restart_interval());
+            // a side table of interval offsets in front of this scan (jls_common.h) spares the search for restart markers
+            StreamOffsetTable table{};
+            static const bool ignore_tables = [] {
+                const char* value = std::getenv("CHARLS_B200_IGNORE_OFFSET_TABLES");
+                return value && value[0] == '1';
+            }();
+            if (!ignore_tables && reader_.scan_offset_table().total == p.interval_count + 1U)
+            {
+                table.total = reader_.scan_offset_table().total;
+                for (uint32_t segment = 0; segment < offset_table_max_segments; ++segment)
+                    table.entry_offsets[segment] = reader_.scan_offset_table().entry_offsets[segment];
+            }
+            const StreamOffsetTable* use_table = table.total != 0 ? &table : nullptr;
             if (deferred && component == 0 && reader_.scan_component_count() == reader_.component_count())
             {
-                check_status(engine().decode_scan_to_host_begin(p, reader_.position(), destination, scan_stride));
+                check_status(engine().decode_scan_to_host_begin(p, reader_.position(), destination, scan_stride, use_table));
                 deferred_ = true;
                 return;
             }
             size_t consumed = 0;
-            check_status(engine().decode_scan_to_host(p, reader_.position(), destination, scan_stride, consumed));
+            check_status(engine().decode_scan_to_host(p, reader_.position(), destination, scan_stride, consumed, use_table));
             reader_.advance(consumed);
 
             component += reader_.scan_component_count();

@@ -87,6 +87,12 @@ struct charls_jpegls_encoder final
         writer_.set_mapping_table_id(static_cast<size_t>(component_index), table_id);
     }
 
+    void offset_table(bool enabled)
+    {
+        check_operation(encoded_component_count_ == 0 && state_ != State::completed);
+        offset_table_ = enabled;
+    }
+
     void restart_interval(uint32_t interval)
     {
         check_operation(encoded_component_count_ == 0 && state_ != State::completed);
@@ -111,6 +117,9 @@ struct charls_jpegls_encoder final
             const size_t limit_bits = 2 * (bits + (bits < 8 ? 8 : bits)); // LIMIT of T.87 (reference src/default_traits.hpp:41-45)
             const size_t per_interval = (limit_bits + 7) / 8 + 4;
             size = add_saturated(size, checked_mul(checked_mul(intervals, per_interval), static_cast<size_t>(frame_info_.component_count)) + 8U);
+            if (offset_table_)
+                size = add_saturated(size, checked_mul(offset_table_bytes(static_cast<uint32_t>(intervals)),
+                                                       static_cast<size_t>(frame_info_.component_count)));
         }
         return size;
     }
@@ -224,6 +233,7 @@ struct charls_jpegls_encoder final
             const size_t plane_bytes = scan_stride * frame_info_.height;
             if (deferred && source_component_count == 1)
             {
+                reserve_offset_table();
                 writer_.write_start_of_scan(1, near_lossless_, interleave_mode_);
                 begin_scan(source, scan_stride, 1);
                 deferred_components_ = 1;
@@ -231,12 +241,14 @@ struct charls_jpegls_encoder final
             }
             for (int32_t component = 0; component < source_component_count; ++component)
             {
+                reserve_offset_table();
                 writer_.write_start_of_scan(1, near_lossless_, interleave_mode_);
                 encode_scan(source + static_cast<size_t>(component) * plane_bytes, scan_stride, 1);
             }
         }
         else
         {
+            reserve_offset_table();
             writer_.write_start_of_scan(source_component_count, near_lossless_, interleave_mode_);
             if (deferred)
             {
@@ -354,8 +366,25 @@ private:
                                                 frame_info_.bits_per_sample, component_count, near_lossless_, interleave_mode_,
                                                 interleave_mode_ != 0 ? color_transformation_ : 0, preset_, restart_interval_);
         size_t written = 0;
-        check_status(engine().encode_scan_from_host(p, source, stride, writer_.remaining_data(), writer_.remaining_size(), written));
+        check_status(engine().encode_scan_from_host(p, source, stride, writer_.remaining_data(), writer_.remaining_size(), written,
+                                                    scan_table_.total != 0 ? &scan_table_ : nullptr));
         writer_.advance(written);
+    }
+
+    // Side table of interval offsets for the scan whose SOS comes next (jls_common.h): the segments are written with empty
+    // entries, the engine fills them in when the scan is coded.
+    void reserve_offset_table()
+    {
+        scan_table_ = HostOffsetTable{};
+        if (!offset_table_ || restart_interval_ == 0)
+            return;
+        const uint32_t lines = restart_interval_ < frame_info_.height ? restart_interval_ : frame_info_.height;
+        const uint32_t intervals = (frame_info_.height + lines - 1) / lines;
+        size_t positions[offset_table_max_segments] = {};
+        writer_.write_offset_table_placeholder(intervals, positions);
+        scan_table_.total = intervals + 1;
+        for (uint32_t segment = 0; segment < offset_table_segment_count(scan_table_.total); ++segment)
+            scan_table_.entries[segment] = writer_.data() + positions[segment];
     }
 
     void begin_scan(const uint8_t* source, size_t stride, int32_t component_count)
@@ -363,7 +392,8 @@ private:
         const CodecParams p = make_codec_params(static_cast<int32_t>(frame_info_.width), static_cast<int32_t>(frame_info_.height),
                                                 frame_info_.bits_per_sample, component_count, near_lossless_, interleave_mode_,
                                                 interleave_mode_ != 0 ? color_transformation_ : 0, preset_, restart_interval_);
-        check_status(engine().encode_scan_from_host_begin(p, source, stride, writer_.remaining_data(), writer_.remaining_size()));
+        check_status(engine().encode_scan_from_host_begin(p, source, stride, writer_.remaining_data(), writer_.remaining_size(),
+                                                          scan_table_.total != 0 ? &scan_table_ : nullptr));
     }
 
     void write_end_of_image()
@@ -385,6 +415,8 @@ private:
     PresetCodingParameters preset_{};
     Engine* engine_{}; // borrowed from the pool on first use
     int32_t deferred_components_{}; // components of the scan that encode_from_buffer_begin has issued and encode_end completes
+    bool offset_table_{};           // write the side table of interval offsets (charlsx_jpegls_encoder_set_offset_table)
+    HostOffsetTable scan_table_{};  // where the current scan's table entries go
 };
 
 extern "C" {
@@ -542,6 +574,11 @@ charls_jpegls_errc charls_jpegls_encoder_rewind(charls_jpegls_encoder* encoder) 
 charls_jpegls_errc charlsx_jpegls_encoder_set_restart_interval(charls_jpegls_encoder* encoder, uint32_t restart_interval) noexcept
 {
     return guarded([&] { check_pointer(encoder)->restart_interval(restart_interval); });
+}
+
+charls_jpegls_errc charlsx_jpegls_encoder_set_offset_table(charls_jpegls_encoder* encoder, int32_t enabled) noexcept
+{
+    return guarded([&] { check_pointer(encoder)->offset_table(enabled != 0); });
 }
 
 charls_jpegls_errc charlsx_jpegls_encoder_encode_from_buffer_begin(charls_jpegls_encoder* encoder, const void* source_buffer,

@@ -215,6 +215,8 @@ void StreamReader::read_segment(uint8_t code, charls_spiff_header* header, bool*
         break;
     default: // APP0-7, APP9-15
         call_application_data_handler(code);
+        if (code == jls::offset_table_marker)
+            read_offset_table_segment();
         skip_rest_of_segment();
         break;
     }
@@ -302,6 +304,46 @@ void StreamReader::read_start_of_scan()
     if ((get8() & 0x0F) != 0) // point transform
         fail(CHARLS_JPEGLS_ERRC_PARAMETER_VALUE_NOT_SUPPORTED);
     state_ = State::bit_stream_section;
+
+    // a side table of interval offsets belongs to the scan that follows it
+    scan_offset_table_ = OffsetTable{};
+    if (pending_offset_entries_ != ~0U && pending_offset_table_.total != 0 && pending_offset_entries_ == pending_offset_table_.total)
+        scan_offset_table_ = pending_offset_table_;
+    pending_offset_table_ = OffsetTable{};
+    pending_offset_entries_ = 0;
+}
+
+// An APP11 segment that carries (part of) the side table of interval offsets (jls_common.h).  Anything that is not exactly
+// that -- another application's APP11, an unknown version, segments out of order -- is not an error: the stream is then
+// decoded like one without a table (the reference does not know the segment at all).
+void StreamReader::read_offset_table_segment()
+{
+    static const uint8_t identifier[8] = {'J', 'L', 'S', '-', 'O', 'F', 'F', 'T'};
+    if (segment_size() < jls::offset_table_header_bytes || std::memcmp(position_, identifier, sizeof(identifier)) != 0)
+        return;
+    const uint8_t* const saved = position_;
+    position_ += sizeof(identifier);
+    const uint32_t version = get8();
+    (void)get8();
+    const uint32_t first = get32(), count = get32(), total = get32();
+    const size_t entries_at = static_cast<size_t>(position_ - begin_);
+    position_ = saved;
+    if (pending_offset_entries_ == ~0U)
+        return;
+    const uint32_t segment = first / jls::offset_table_entries_per_segment;
+    const bool well_formed = version == 1 && total >= 2 && count >= 1 && first < total && first == pending_offset_entries_ &&
+                             first % jls::offset_table_entries_per_segment == 0 && segment < jls::offset_table_max_segments &&
+                             count == (total - first < jls::offset_table_entries_per_segment ? total - first : jls::offset_table_entries_per_segment) &&
+                             segment_size() == jls::offset_table_header_bytes + static_cast<size_t>(count) * 4U &&
+                             (first == 0 || total == pending_offset_table_.total);
+    if (!well_formed)
+    {
+        pending_offset_entries_ = ~0U;
+        return;
+    }
+    pending_offset_table_.total = total;
+    pending_offset_table_.entry_offsets[segment] = entries_at;
+    pending_offset_entries_ += count;
 }
 
 // reference jpeg_stream_reader.cpp:488-606

@@ -5,6 +5,7 @@
 // data itself is never looked at here -- the CUDA engine reports how many bytes a scan consumed.
 #pragma once
 
+#include "../jls_common.h"
 #include "abi_support.hpp"
 
 #include <vector>
@@ -43,6 +44,15 @@ public:
     int32_t scan_near_lossless() const noexcept { return scan_near_lossless_; }
     int32_t color_transformation() const noexcept { return color_transformation_; }
     uint32_t restart_interval() const noexcept { return restart_interval_; }
+
+    // The side table of interval offsets found in front of the current scan's SOS (jls_common.h), if it was complete and
+    // well formed: entry_offsets[s] = offset in the source of segment s's first entry.  total == 0: none.
+    struct OffsetTable
+    {
+        uint32_t total{};
+        size_t entry_offsets[jls::offset_table_max_segments]{};
+    };
+    const OffsetTable& scan_offset_table() const noexcept { return scan_offset_table_; }
 
     // position of the first entropy-coded byte of the current scan, relative to the start of the source
     size_t position() const noexcept { return static_cast<size_t>(position_ - begin_); }
@@ -137,6 +147,7 @@ private:
     uint32_t read_number_of_lines();
     void read_application_data8(charls_spiff_header* header, bool* found);
     void call_application_data_handler(uint8_t code) const;
+    void read_offset_table_segment();
     void find_define_number_of_lines();
     void set_height(uint32_t height, bool final_update);
     void set_width(uint32_t width);
@@ -164,6 +175,9 @@ private:
     uint32_t restart_interval_{};
     bool dnl_expected_{};
     int32_t compressed_data_format_{};
+    OffsetTable pending_offset_table_{}; // segments seen since the last SOS
+    uint32_t pending_offset_entries_{};  // entries they hold so far; ~0 after a malformed segment
+    OffsetTable scan_offset_table_{};
     charls_at_comment_handler comment_handler_{};
     void* comment_context_{};
     charls_at_application_data_handler application_data_handler_{};

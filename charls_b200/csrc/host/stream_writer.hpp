@@ -8,6 +8,8 @@
 
 #include <array>
 #include <vector>
+#include "../jls_common.h"
+
 #include <cstring>
 
 namespace jls::host {
@@ -173,6 +175,32 @@ public:
             put32(restart_interval);
         }
     }
+
+    // Reserves the side table of interval offsets (jls_common.h) for the scan whose SOS follows: headers are written, the
+    // entries stay zero.  entry_positions[s] = offset in the destination of segment s's first entry.
+    void write_offset_table_placeholder(uint32_t intervals, size_t (&entry_positions)[jls::offset_table_max_segments])
+    {
+        const uint32_t total = intervals + 1U;
+        uint32_t first = 0;
+        for (uint32_t segment = 0; first < total; ++segment)
+        {
+            const uint32_t count = total - first < jls::offset_table_entries_per_segment ? total - first : jls::offset_table_entries_per_segment;
+            begin_segment(jls::offset_table_marker, jls::offset_table_header_bytes + static_cast<size_t>(count) * 4U);
+            static const uint8_t identifier[8] = {'J', 'L', 'S', '-', 'O', 'F', 'F', 'T'};
+            put_bytes(identifier, sizeof(identifier));
+            put8(1);
+            put8(0);
+            put32(first);
+            put32(count);
+            put32(total);
+            entry_positions[segment] = position_;
+            std::memset(data_ + position_, 0, static_cast<size_t>(count) * 4U);
+            position_ += static_cast<size_t>(count) * 4U;
+            first += count;
+        }
+    }
+
+    uint8_t* data() const noexcept { return data_; }
 
     void write_start_of_scan(int32_t component_count, int32_t near_lossless, int32_t interleave_mode)
     {

@@ -483,6 +483,13 @@ struct BitReader
     // those and never checks that all bits of the code it then skips were valid (src/scan_decoder.hpp:144-152, 58-64): the
     // last code word of an interval may end in up to seven zero bits that are not in the stream (interval_end_status).
     int32_t last_code_bits;
+    bool marker_inside; // a 0xFF followed by a byte >= 0x80 was read as data
+
+    JLS_HD bool leftover_is_zero_padding() // see FastReaderT
+    {
+        refill();
+        return pos >= end && !residue();
+    }
 
     JLS_HD uint32_t load_word(const uint32_t* w) const
     {
@@ -498,6 +505,7 @@ struct BitReader
         pos = begin;
         end = end_;
         last_code_bits = 255;
+        marker_inside = false;
         const uintptr_t address = reinterpret_cast<uintptr_t>(begin);
         wptr = reinterpret_cast<const uint32_t*>(address & ~static_cast<uintptr_t>(3));
         shift = static_cast<uint32_t>(address & 3U) * 8U;
@@ -507,6 +515,8 @@ struct BitReader
 
     JLS_HD void append_byte(uint32_t b, bool is_virtual)
     {
+        if (prev_ff && (b & 0x80U) != 0)
+            marker_inside = true; // see FastReaderT::refill_once
         const int32_t take = prev_ff ? 7 : 8;
         cache |= static_cast<uint64_t>(b & (0xFFU >> (8 - take))) << (64 - take - valid);
         valid += take;
@@ -768,9 +778,15 @@ JLS_HD void color_inverse(int32_t transform, int32_t type_mask, int32_t& c0, int
 // Lines are kept as uint16_t[components][width + 2] x 2 in global scratch; index 0 and width + 1 are the edge samples
 // (reference src/scan_codec.hpp:189-195).
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int32_t general_context_count = 365;
+
 struct GeneralState
 {
-    RegularContext contexts[365];
+    // The 365 regular contexts live where the caller puts them: the kernels hand every thread 365 * 16 bytes of SHARED memory.
+    // As a member array they were thread-local memory, which interleaves the 32 lanes of a warp word by word -- with one
+    // restart interval per scan only one lane of a warp works, every context access touched a cache line of its own and
+    // the 187 KB a warp's contexts then span did not stay in L1 (31 -> ~1 MPix/s per stream, profiles/r2_notes.md).
+    RegularContext* contexts;
     RunContext run_contexts[2];
     int32_t run_index;
     bool bad;
@@ -778,7 +794,7 @@ struct GeneralState
     JLS_HD void reset(const CodecParams& p) // reference src/scan_codec.hpp:163-174
     {
         const RegularContext initial = {p.a_init, 0, 0, 1};
-        for (int32_t i = 0; i < 365; ++i)
+        for (int32_t i = 0; i < general_context_count; ++i)
             contexts[i] = initial;
         for (int32_t i = 0; i < 2; ++i)
         {
@@ -801,17 +817,25 @@ template<bool LOSSLESS>
 JLS_HD_NOINLINE void general_encode_line(const CodecParams& p, GeneralState& s, BitWriter& bw, uint16_t* cur,
                                          const uint16_t* prev)
 {
+    // the neighbourhood slides along in registers, see general_decode_line
     const int32_t width = p.width;
     int32_t index = 1;
+    int32_t ra = cur[0], rc = prev[0], rb = prev[1], rd = prev[2];
     while (index <= width)
     {
-        const int32_t ra = cur[index - 1], rc = prev[index - 1], rb = prev[index], rd = prev[index + 1];
+        const int32_t rd_next = prev[index + 2 <= width + 1 ? index + 2 : width + 1];
         const int32_t qs = s.context_id(p, ra, rb, rc, rd);
         if (qs != 0)
         {
             const int32_t sign = bit_wise_sign(qs);
-            cur[index] = static_cast<uint16_t>(encode_regular_sample<LOSSLESS>(p, bw, s.contexts[apply_sign(qs, sign)], sign,
-                                                                               cur[index], predict_med(ra, rb, rc), s.bad));
+            const int32_t x = encode_regular_sample<LOSSLESS>(p, bw, s.contexts[apply_sign(qs, sign)], sign, cur[index],
+                                                              predict_med(ra, rb, rc), s.bad);
+            if (!LOSSLESS)
+                cur[index] = static_cast<uint16_t>(x); // the reconstructed value is the next line's neighbourhood
+            ra = x;
+            rc = rb;
+            rb = rd;
+            rd = rd_next;
             ++index;
             continue;
         }
@@ -830,22 +854,28 @@ JLS_HD_NOINLINE void general_encode_line(const CodecParams& p, GeneralState& s, 
         index += run_length;
         const int32_t x = cur[index];
         const int32_t rb2 = prev[index];
+        int32_t reconstructed;
         if (iabs(ra - rb2) <= p.near) // reference src/scan_encoder_core.hpp:118-131
         {
             const int32_t e = compute_error_value<LOSSLESS>(p, x - ra);
             encode_run_interruption_error(p, bw, s.run_contexts[1], 1, e, s.run_index);
-            cur[index] = static_cast<uint16_t>(reconstruct<LOSSLESS>(p, ra, e));
+            reconstructed = reconstruct<LOSSLESS>(p, ra, e);
         }
         else
         {
             const int32_t sg = sign_of(rb2 - ra);
             const int32_t e = compute_error_value<LOSSLESS>(p, (x - rb2) * sg);
             encode_run_interruption_error(p, bw, s.run_contexts[0], 0, e, s.run_index);
-            cur[index] = static_cast<uint16_t>(reconstruct<LOSSLESS>(p, rb2, e * sg));
+            reconstructed = reconstruct<LOSSLESS>(p, rb2, e * sg);
         }
+        cur[index] = static_cast<uint16_t>(reconstructed);
         if (s.run_index > 0)
             --s.run_index;
         ++index;
+        ra = reconstructed;
+        rc = rb2;
+        rb = prev[index <= width + 1 ? index : width + 1];
+        rd = prev[index + 1 <= width + 1 ? index + 1 : width + 1];
     }
 }
 
@@ -921,17 +951,26 @@ template<bool LOSSLESS>
 JLS_HD_NOINLINE void general_decode_line(const CodecParams& p, GeneralState& s, BitReader& br, uint16_t* cur,
                                          const uint16_t* prev)
 {
+    // The neighbourhood slides along in registers: Ra is the sample just decoded, Rc and Rb were Rb and Rd one pixel ago,
+    // and the only load per pixel -- Rd of the NEXT pixel -- is issued a whole pixel before it is needed.  (Reading Ra back
+    // from the line that was stored to a moment ago put a trip to L2 on the critical path of every pixel.)
     const int32_t width = p.width;
     int32_t index = 1;
+    int32_t ra = cur[0], rc = prev[0], rb = prev[1], rd = prev[2];
     while (index <= width && !s.bad)
     {
-        const int32_t ra = cur[index - 1], rc = prev[index - 1], rb = prev[index], rd = prev[index + 1];
+        const int32_t rd_next = prev[index + 2 <= width + 1 ? index + 2 : width + 1];
         const int32_t qs = s.context_id(p, ra, rb, rc, rd);
         if (qs != 0)
         {
             const int32_t sign = bit_wise_sign(qs);
-            cur[index] = static_cast<uint16_t>(
-                decode_regular_sample<LOSSLESS>(p, br, s.contexts[apply_sign(qs, sign)], sign, predict_med(ra, rb, rc), s.bad));
+            const int32_t x =
+                decode_regular_sample<LOSSLESS>(p, br, s.contexts[apply_sign(qs, sign)], sign, predict_med(ra, rb, rc), s.bad);
+            cur[index] = static_cast<uint16_t>(x);
+            ra = x;
+            rc = rb;
+            rb = rd;
+            rd = rd_next;
             ++index;
             continue;
         }
@@ -947,19 +986,26 @@ JLS_HD_NOINLINE void general_decode_line(const CodecParams& p, GeneralState& s, 
         if (index - 1 == width)
             return;
         const int32_t rb2 = prev[index];
+        int32_t x;
         if (iabs(ra - rb2) <= p.near)
         {
             const int32_t e = decode_run_interruption_error(p, br, s.run_contexts[1], 1, s.run_index, s.bad);
-            cur[index] = static_cast<uint16_t>(reconstruct<LOSSLESS>(p, ra, e));
+            x = reconstruct<LOSSLESS>(p, ra, e);
         }
         else
         {
             const int32_t e = decode_run_interruption_error(p, br, s.run_contexts[0], 0, s.run_index, s.bad);
-            cur[index] = static_cast<uint16_t>(reconstruct<LOSSLESS>(p, rb2, e * sign_of(rb2 - ra)));
+            x = reconstruct<LOSSLESS>(p, rb2, e * sign_of(rb2 - ra));
         }
+        cur[index] = static_cast<uint16_t>(x);
         if (s.run_index > 0)
             --s.run_index;
         ++index;
+        // the window jumped: reload it (index <= width + 1, so index + 1 may be the slot behind the right edge sample)
+        ra = x;
+        rc = rb2;
+        rb = prev[index <= width + 1 ? index : width + 1];
+        rd = prev[index + 1 <= width + 1 ? index + 1 : width + 1];
     }
 }
 

@@ -57,6 +57,42 @@ struct CodecParams
     uint32_t interval_count;   // ceil(height / lines_per_interval)
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Optional side table of interval offsets (extension; not in the reference, which neither writes nor looks at it -- to every
+// other JPEG-LS decoder it is an application data segment to skip).  One or more APP11 segments in front of a scan's SOS:
+//   "JLS-OFFT" (8 bytes) | version = 1 | 0 | first entry (u32) | entries in this segment (u32) | entries in all (u32) | entries
+// all big endian.  Entry j < N (N = number of restart intervals of the scan) is the offset of the first byte of interval j
+// from the first entropy-coded byte of the scan, entry N the offset of the marker that closes the scan.  With the table a
+// decoder finds its intervals without searching the stream for restart markers (the three marker kernels), and a rank
+// that decodes only some lines knows which bytes to fetch.  It is checked against the stream before it is believed
+// (k_offsets_from_table, interval_end_status); a stream that does not agree with its table is decoded as if it had none.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint8_t offset_table_marker = 0xEB; // APP11
+constexpr uint32_t offset_table_header_bytes = 22;
+constexpr uint32_t offset_table_entries_per_segment = (65533U - offset_table_header_bytes) / 4U;
+constexpr uint32_t offset_table_max_segments = 8; // 131 016 entries: heights go up to 100 000
+constexpr int32_t errc_offset_table_rejected = 250; // internal: never leaves the engine
+
+inline uint32_t offset_table_segment_count(uint32_t entries)
+{
+    return (entries + offset_table_entries_per_segment - 1U) / offset_table_entries_per_segment;
+}
+
+// bytes the table of a scan with `intervals` restart intervals takes in the stream (marker + length + header + entries)
+inline size_t offset_table_bytes(uint32_t intervals)
+{
+    const uint32_t entries = intervals + 1U;
+    return static_cast<size_t>(offset_table_segment_count(entries)) * (4U + offset_table_header_bytes) + static_cast<size_t>(entries) * 4U;
+}
+
+// Where the entries of a table sit in device memory (decode) / go (encode): segment s holds entries
+// [s * offset_table_entries_per_segment, ...), big endian, at entries[s].
+struct OffsetTableRef
+{
+    uint8_t* entries[offset_table_max_segments];
+    uint32_t total; // entries in all segments = intervals + 1; 0 = no table
+};
+
 // One image (or one plane of an ILV-none image) to code: where the samples live and where the entropy bytes go.
 struct ScanJob
 {
@@ -72,6 +108,7 @@ struct ScanJob
     uint64_t* interval_offset; // encode: exclusive scan of (bytes + marker)            [interval_count + 1]
                                // decode: start offset of every interval in stream_in   [interval_count + 1]
     uint16_t* line_scratch;   // general (2-D) path: 2 * components * (width + 2) samples per interval
+    OffsetTableRef offset_table; // encode: where to write the side table (total = 0: none); decode: the table to check and use
     uint64_t* status;         // first-error key: (interval << 8) | charls_jpegls_errc, ~0 when no error
     uint64_t* result;         // [0] encode: total bytes written; decode: bytes consumed by the scan
                               // [1] decode: code of the marker that closes the scan

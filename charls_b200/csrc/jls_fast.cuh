@@ -50,9 +50,11 @@
 #ifndef JLS_FMA_ADDS
 #define JLS_FMA_ADDS 1
 #endif
-// 1: the one-component 8-bit decoders top their read window up every 8 samples instead of every 4 (FastLineDecoder)
+// 1: the one-component 8-bit decoders top their read window up every 8 samples instead of every 4 (FastLineDecoder).
+// Measured (profiles/r2_notes.md): no gain -- what a top-up costs the warp is its number of refill iterations, and eight
+// samples need two where four need one; cfg2 decoder 6.88 ms (4) against 6.95 ms (8).  Off.
 #ifndef JLS_TOP_UP_8
-#define JLS_TOP_UP_8 1
+#define JLS_TOP_UP_8 0
 #endif
 
 namespace jls {
@@ -786,6 +788,10 @@ struct FastReaderT
             {
                 const bool is_virtual = i >= remaining;
                 const uint32_t b = is_virtual ? 0U : (w >> (24 - 8 * i)) & 0xFFU;
+                // 0xFF followed by a byte with its top bit set is a marker, and an interval never contains one: the marker
+                // search would have ended it there.  (Only a wrong side table of offsets can lead a reader into one.)
+                if (prev_ff && (b & 0x80U) != 0)
+                    bad |= 2U;
                 const int32_t take = prev_ff ? 7 : 8;
                 bits = (bits << take) | (b & (0xFFU >> (8 - take)));
                 count += take;
@@ -865,6 +871,15 @@ struct FastReaderT
 
     // true when bits that were not consumed are not all zero
     JLS_HD bool residue() const { return (c3 | c2 | c1 | c0) != 0; }
+
+    // Side-table mode (interval_end_status, strict): true when what is left of the interval after the last symbol is known
+    // to be zero bits only -- everything real has been moved into the window (refills first) and nothing in it is set.  A
+    // marker needs a 0xFF, so the marker search would have found the same interval.
+    JLS_HD bool leftover_is_zero_padding()
+    {
+        refill();
+        return remaining <= 0 && !residue();
+    }
 
     // whole unread bytes left in the interval after the last decoded symbol
     JLS_HD int32_t unread_bytes() const
@@ -1290,9 +1305,8 @@ struct FastLineEncoder : FastLineState<NC, LUT_MODE, DEPTH>
 template<int NC, bool LOSSLESS, int LUT_MODE = lut_none, int DEPTH = 0>
 struct FastLineDecoder : FastLineState<NC, LUT_MODE, DEPTH>
 {
-    // One-component lines in 8-bit containers code a few bits per sample: eight samples between two top-ups with code words
-    // of up to 12 bits on the unchecked path (a top-up costs the warp ~35 instructions whether one lane or all need a word);
-    // everything else keeps four samples of up to 24 bits.  JLS_TOP_UP_8 = 0 switches back (A/B).
+    // JLS_TOP_UP_8 (A/B, off): one-component lines in 8-bit containers with eight samples between two top-ups and code words
+    // of up to 12 bits on the unchecked path; everything else four samples of up to 24 bits.
     static constexpr bool long_cadence = JLS_TOP_UP_8 && NC == 1 && LUT_MODE == lut_full;
     FastReaderT<NC == 3 ? JLS_READER_DEPTH_NC3 : 1, long_cadence ? 12 : 24> br;
     // 2 * (pixels of the current run still to be output) + (1 if a run-interruption pixel follows the run): one

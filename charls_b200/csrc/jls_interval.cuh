@@ -141,12 +141,17 @@ JLS_HD IntervalResult encode_interval_fast(const CodecParams& p, const ScanJob& 
 }
 
 // What the reference checks when an interval / the scan ends (src/scan_decoder.hpp:71-89,335-349).
+// strict: the interval came from a side table of offsets, not from the marker search.  It then counts only if the search
+// would have produced the very same interval, i.e. if no marker hides in bytes the decoder did not look at: whatever is
+// left after the last symbol must be zero padding.  Anything else rejects the table (the engine decodes again without it).
 template<typename Reader>
-JLS_HD int32_t interval_end_status(const CodecParams& p, const Reader& br, bool bad, uint32_t interval,
-                                   bool closing_marker_found = true)
+JLS_HD int32_t interval_end_status(const CodecParams& p, Reader& br, bool bad, uint32_t interval,
+                                   bool closing_marker_found = true, bool strict = false)
 {
     if (bad)
         return err_invalid_data;
+    if (strict && !br.leftover_is_zero_padding())
+        return errc_offset_table_rejected;
     if (br.overrun())
     {
         // Bits beyond the end of the interval were consumed.  The reference throws invalid_data when it needs bits and finds
@@ -240,7 +245,7 @@ JLS_HD IntervalResult decode_interval_fast(const CodecParams& p, const ScanJob& 
             fast_store_pixel<NC, S>(p, line, x, dec.ra);
         }
     }
-    result.errc = interval_end_status(p, dec.br, dec.bad(), interval, closing_marker_found);
+    result.errc = interval_end_status(p, dec.br, dec.bad(), interval, closing_marker_found, job.offset_table.total != 0);
     return result;
 }
 
@@ -259,7 +264,7 @@ JLS_HD void general_set_edges(uint16_t* cur, uint16_t* prev, int32_t nc, int32_t
 
 template<bool LOSSLESS>
 JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval,
-                                                       size_t slot_bytes)
+                                                       size_t slot_bytes, RegularContext* contexts)
 {
     const int32_t width = p.width, ps = width + 2, nc = p.components;
     const size_t per_interval = static_cast<size_t>(2) * nc * ps;
@@ -268,6 +273,7 @@ JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, con
         lines[i] = 0;
 
     GeneralState state;
+    state.contexts = contexts; // general_context_count entries owned by this thread (shared memory in the kernels)
     state.reset(p);
     state.bad = false;
     int32_t run_index[4] = {0, 0, 0, 0};
@@ -323,7 +329,8 @@ JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, con
 }
 
 template<bool LOSSLESS>
-JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval)
+JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval,
+                                                       RegularContext* contexts)
 {
     IntervalResult result = {err_none, 0};
     const uint64_t begin = job.interval_offset[2 * static_cast<size_t>(interval)];
@@ -343,6 +350,7 @@ JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, con
         lines[i] = 0;
 
     GeneralState state;
+    state.contexts = contexts; // general_context_count entries owned by this thread (shared memory in the kernels)
     state.reset(p);
     state.bad = false;
     int32_t run_index[4] = {0, 0, 0, 0};
@@ -390,7 +398,7 @@ JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, con
             }
         }
     }
-    result.errc = interval_end_status(p, br, state.bad, interval, closing_marker_found);
+    result.errc = interval_end_status(p, br, state.bad || br.marker_inside, interval, closing_marker_found, job.offset_table.total != 0);
     return result;
 }
 

@@ -39,6 +39,10 @@ namespace {
 #if !defined(JLS_UNROLL_DECODER)
 #define JLS_UNROLL_DECODER 0
 #endif
+// 1: the encoder's tiles are loaded with TMA bulk copies instead of cp.async (A/B, see jls_tile.cuh)
+#if !defined(JLS_TILE_LOAD_BULK)
+#define JLS_TILE_LOAD_BULK 0
+#endif
 constexpr int fast_block_threads = JLS_FAST_BLOCK_THREADS;
 constexpr int general_block_threads = 32;
 
@@ -137,14 +141,17 @@ template<int NC, bool LOSSLESS, typename S, int DEPTH>
 __global__ void __launch_bounds__(fast_block_threads, NC == 1 ? JLS_ENCODE_MIN_BLOCKS_NC1 : NC == 3 ? 26 : 28)
     k_encode_tiled(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
-    constexpr int TW = TileShape<NC, S, true>::words, SW = TileShape<NC, S, true>::stride_words;
+    // JLS_TILE_LOAD_BULK (A/B, jls_tile.cuh): rows land 16-byte aligned (TW + 4 words apart) through TMA bulk copies
+    constexpr bool bulk = JLS_TILE_LOAD_BULK != 0;
+    constexpr int TW = TileShape<NC, S, true>::words, SW = bulk ? TW + 4 : TileShape<NC, S, true>::stride_words;
     constexpr int pixels_per_tile = TW * 4 / static_cast<int>(sizeof(S)) / NC;
     constexpr int warps = fast_block_threads / 32;
     constexpr int first_context = NC == 1 ? 1 : 0; // scalar lines never use context 0 (FastLineState::first_context)
     // Two tile buffers: the next tile is in flight while this one is coded.  (One buffer and a wait per tile leaves room
     // for more resident blocks -- 31 instead of 21 for three-component pixels -- and measured 3 % slower.)
     __shared__ RegularContext contexts[(5 - first_context) * fast_block_threads];
-    __shared__ uint32_t tiles[warps][2][32 * SW];
+    __shared__ __align__(16) uint32_t tiles[warps][2][32 * SW];
+    __shared__ uint64_t tile_ready[warps][2]; // bulk: one mbarrier per tile buffer
     extern __shared__ uint8_t context_lut[]; // lut_last + 1 entries, sized at launch (tiled_dynamic_shared_bytes)
 
     // the host only picks this kernel when T3 fits; 8-bit containers get an entry for every sample value (no clamp)
@@ -200,18 +207,40 @@ __global__ void __launch_bounds__(fast_block_threads, NC == 1 ? JLS_ENCODE_MIN_B
     const int32_t transform = h.transform;
     const bool mask_needed = DEPTH == 0 && h.bits != static_cast<int32_t>(8 * sizeof(S));
 
-    tile_load_async<TW>(tiles[warp][0], pixels, stride, first_line, last_line, row_bytes, 0, lane);
+    // bulk copies need whole tiles, all 32 lines and 16-byte aligned rows; the last (partial) tile of a line and everything
+    // else goes through cp.async
+    const bool bulk_rows = bulk && first_line + 31U <= last_line && stride % 16 == 0 && reinterpret_cast<uintptr_t>(pixels) % 16 == 0;
+    const auto load_tile = [&](int32_t index) {
+        if (bulk_rows && (index + 1) * (TW * 4) <= row_bytes)
+            tile_load_bulk<TW>(static_cast<uint32_t>(__cvta_generic_to_shared(tiles[warp][index & 1])), SW * 4U,
+                               static_cast<uint32_t>(__cvta_generic_to_shared(&tile_ready[warp][index & 1])), pixels, stride, first_line,
+                               index, lane);
+        else
+            tile_load_async<TW, SW>(tiles[warp][index & 1], pixels, stride, first_line, last_line, row_bytes, index, lane);
+    };
+    if (bulk)
+    {
+        if (lane < 2)
+            mbarrier_init(static_cast<uint32_t>(__cvta_generic_to_shared(&tile_ready[warp][lane])), 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+    load_tile(0);
     for (int32_t t = 0; t < tile_count; ++t)
     {
         if (t + 1 < tile_count)
         {
-            tile_load_async<TW>(tiles[warp][(t + 1) & 1], pixels, stride, first_line, last_line, row_bytes, t + 1, lane);
+            if (bulk)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the buffer's last readers were ordinary loads
+            load_tile(t + 1);
             cp_async_wait<1>();
         }
         else
         {
             cp_async_wait<0>();
         }
+        if (bulk_rows && (t + 1) * (TW * 4) <= row_bytes)
+            mbarrier_wait(static_cast<uint32_t>(__cvta_generic_to_shared(&tile_ready[warp][t & 1])), static_cast<uint32_t>(t >> 1) & 1U);
         __syncwarp();
         if (active)
         {
@@ -411,7 +440,7 @@ __global__ void __launch_bounds__(fast_block_threads)
     }
     if (coding)
     {
-        const int32_t errc = interval_end_status(p, dec.br, dec.bad(), interval, closing_marker_found);
+        const int32_t errc = interval_end_status(p, dec.br, dec.bad(), interval, closing_marker_found, job.offset_table.total != 0);
         if (errc != err_none)
             report_error(job, interval, errc);
     }
@@ -420,15 +449,19 @@ __global__ void __launch_bounds__(fast_block_threads)
 // ---------------------------------------------------------------------------------------------------------------------
 // General path: one thread per restart interval, full 2-D LOCO-I (365 contexts in local memory).
 // ---------------------------------------------------------------------------------------------------------------------
+// Dynamic shared memory: general_context_count contexts (5840 bytes) per thread that has an interval -- 32 in a full
+// block (one block per SM then), one for scans without restart markers (one interval per scan, one working lane per warp).
 template<bool LOSSLESS>
 __global__ void __launch_bounds__(general_block_threads)
     k_encode_general(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
+    extern __shared__ __align__(16) uint8_t general_shared[];
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t interval = blockIdx.x * general_block_threads + threadIdx.x;
     if (interval >= p.interval_count)
         return;
-    const IntervalResult r = encode_interval_general<LOSSLESS>(p, job, interval, slot_bytes);
+    RegularContext* contexts = reinterpret_cast<RegularContext*>(general_shared) + threadIdx.x * general_context_count;
+    const IntervalResult r = encode_interval_general<LOSSLESS>(p, job, interval, slot_bytes, contexts);
     job.interval_bytes[interval] = r.bytes;
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
@@ -438,11 +471,13 @@ template<bool LOSSLESS>
 __global__ void __launch_bounds__(general_block_threads)
     k_decode_general(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
 {
+    extern __shared__ __align__(16) uint8_t general_shared[];
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t interval = blockIdx.x * general_block_threads + threadIdx.x;
     if (interval >= p.interval_count)
         return;
-    const IntervalResult r = decode_interval_general<LOSSLESS>(p, job, interval);
+    RegularContext* contexts = reinterpret_cast<RegularContext*>(general_shared) + threadIdx.x * general_context_count;
+    const IntervalResult r = decode_interval_general<LOSSLESS>(p, job, interval, contexts);
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
 }
@@ -811,6 +846,85 @@ __global__ void __launch_bounds__(marker_block_threads)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Side table of interval offsets (jls_common.h)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t* offset_table_entry(const OffsetTableRef& table, uint32_t index)
+{
+    return table.entries[index / offset_table_entries_per_segment] + static_cast<size_t>(index % offset_table_entries_per_segment) * 4U;
+}
+
+// Encode: interval_offset[0 .. N] (k_scan_offsets) -> big-endian entries in the reserved segments of the stream header
+__global__ void k_write_offset_table(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job.offset_table.total != p.interval_count + 1U || j > p.interval_count)
+        return;
+    const uint64_t total = job.interval_offset[p.interval_count];
+    if (total > job.stream_out_capacity || total >= (1ULL << 32))
+        return; // nothing was written / does not fit 32-bit entries: the entries stay zero and no decoder will believe them
+    const uint32_t v = static_cast<uint32_t>(job.interval_offset[j]);
+    uint8_t* entry = offset_table_entry(job.offset_table, j);
+    entry[0] = static_cast<uint8_t>(v >> 24);
+    entry[1] = static_cast<uint8_t>(v >> 16);
+    entry[2] = static_cast<uint8_t>(v >> 8);
+    entry[3] = static_cast<uint8_t>(v);
+}
+
+__device__ __forceinline__ uint32_t read_offset_entry(const OffsetTableRef& table, uint32_t index)
+{
+    const uint8_t* e = offset_table_entry(table, index);
+    return (static_cast<uint32_t>(e[0]) << 24) | (static_cast<uint32_t>(e[1]) << 16) | (static_cast<uint32_t>(e[2]) << 8) | e[3];
+}
+
+// Decode: the table instead of the three marker kernels.  Thread i checks what the table says about interval i against the
+// stream -- offsets ascending and inside the stream, FF D0+(i mod 8) directly in front of the next interval, a marker
+// where the scan is said to end -- and fills interval_offset / marker_codes / marker_totals exactly as k_marker_write
+// would have.  Any disagreement rejects the table for this job (errc_offset_table_rejected): the engine then decodes the
+// stream again by searching for the markers.  What the table cannot know -- a marker INSIDE an interval -- the decoders
+// notice themselves (a 0xFF followed by a byte >= 0x80 is an error to their bit readers; interval_end_status, strict).
+__global__ void k_offsets_from_table(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
+                                     uint32_t* __restrict__ marker_totals, uint8_t* __restrict__ marker_codes)
+{
+    const ScanJob& job = jobs[blockIdx.y];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = p.interval_count;
+    if (i >= n)
+        return;
+    const uint8_t* data = job.stream_in;
+    assume_global(data);
+    const uint64_t begin = read_offset_entry(job.offset_table, i);
+    const uint64_t next = read_offset_entry(job.offset_table, i + 1);
+    const bool last = i + 1 == n;
+    bool ok = (i != 0 || begin == 0) && next >= begin + (last ? 0U : 2U) && next + (last ? 2U : 0U) <= job.stream_in_size;
+    uint64_t end = next;
+    uint8_t code = 0;
+    if (ok && last)
+    {
+        code = data[next + 1];
+        ok = data[next] == 0xFF && code >= 0x80 && code != 0xFF;
+    }
+    else if (ok)
+    {
+        end = next - 2;
+        code = data[next - 1];
+        ok = data[end] == 0xFF && code == 0xD0U + (i & 7U);
+        // fill bytes in front of a marker (T.81 B.1.1.2) belong to the marker: the search would have ended the interval there
+        ok = ok && (end == begin || data[end - 1] != 0xFF);
+    }
+    if (!ok)
+    {
+        report_error(job, 0, errc_offset_table_rejected);
+        return;
+    }
+    job.interval_offset[2 * static_cast<size_t>(i)] = begin;
+    job.interval_offset[2 * static_cast<size_t>(i) + 1] = end;
+    marker_codes[static_cast<size_t>(blockIdx.y) * n + i] = code;
+    if (i == 0)
+        marker_totals[blockIdx.y] = n;
+}
+
 // one thread per job: bytes consumed by the scan, its closing marker, and the data-ends-early case
 __global__ void k_decode_finish(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs,
                                 const uint32_t* __restrict__ marker_totals, const uint8_t* __restrict__ marker_codes,
@@ -859,19 +973,20 @@ __global__ void k_init_status(const ScanJob* __restrict__ jobs, uint32_t job_cou
 // Batch encode: completes every frame's stream: header bytes in front of the entropy-coded data, EOI behind it.
 // One warp per frame.  stream_out points at the first entropy byte, i.e. header_size bytes into the frame's stream.
 __global__ void k_wrap_frames(const ScanJob* __restrict__ jobs, const uint8_t* __restrict__ header, uint32_t header_size,
-                              uint32_t job_count)
+                              uint32_t job_count, int parts)
 {
     const uint32_t j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (j >= job_count)
         return;
     const ScanJob& job = jobs[j];
-    if (job.result[0] > job.stream_out_capacity)
-        return;
-    uint8_t* begin = job.stream_out - header_size;
-    for (uint32_t i = lane; i < header_size; i += 32)
-        begin[i] = header[i];
-    if (lane == 0)
+    if ((parts & wrap_header) != 0 && job.stream_out_capacity != 0) // capacity 0: not even header + EOI fit
+    {
+        uint8_t* begin = job.stream_out - header_size;
+        for (uint32_t i = lane; i < header_size; i += 32)
+            begin[i] = header[i];
+    }
+    if ((parts & wrap_end_of_image) != 0 && job.result[0] <= job.stream_out_capacity && lane == 0)
     {
         job.stream_out[job.result[0]] = 0xFF;
         job.stream_out[job.result[0] + 1] = 0xD9;
@@ -928,6 +1043,23 @@ cudaError_t launch_with_shared(Kernel kernel, dim3 grid, dim3 block, size_t dyna
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     ++t_kernel_launches;
     return cudaGetLastError();
+}
+
+// General-path kernels: shared memory for the contexts of the threads of a block that have an interval (up to 32 x 5840
+// bytes, which needs the opt-in limit).
+template<typename Kernel, typename... Args>
+cudaError_t launch_general(Kernel kernel, dim3 grid, const CodecParams& p, cudaStream_t stream, Args... args)
+{
+    const size_t working = p.interval_count < static_cast<uint32_t>(general_block_threads) ? p.interval_count : general_block_threads;
+    const size_t bytes = working * general_context_count * sizeof(RegularContext);
+    if (bytes > 48U * 1024U)
+    {
+        const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(bytes));
+        if (e != cudaSuccess)
+            return e;
+    }
+    return launch_with_shared(kernel, grid, dim3(general_block_threads), bytes, stream, args...);
 }
 
 // The tile kernels keep the context-index table |Q(-Ra)| in dynamic shared memory: Ra = 0 .. 255 for 8-bit containers (no
@@ -1101,7 +1233,7 @@ size_t marker_scratch_bytes(size_t job_count, size_t max_stream_bytes) noexcept
     } while (0)
 
 cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t slot_bytes,
-                          cudaStream_t stream, cudaEvent_t* coder_events, bool rows_word_aligned)
+                          cudaStream_t stream, cudaEvent_t* coder_events, bool rows_word_aligned, bool offset_tables)
 {
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
     const bool lossless = p.near == 0;
@@ -1117,13 +1249,15 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
     {
         const dim3 grid((p.interval_count + general_block_threads - 1) / general_block_threads, job_count);
         if (lossless)
-            JLS_TRY(launch(k_encode_general<true>, grid, dim3(general_block_threads), stream, p, device_jobs, slot_bytes));
+            JLS_TRY(launch_general(k_encode_general<true>, grid, p, stream, p, device_jobs, slot_bytes));
         else
-            JLS_TRY(launch(k_encode_general<false>, grid, dim3(general_block_threads), stream, p, device_jobs, slot_bytes));
+            JLS_TRY(launch_general(k_encode_general<false>, grid, p, stream, p, device_jobs, slot_bytes));
     }
     if (coder_events)
         JLS_TRY(cudaEventRecord(coder_events[1], stream));
     JLS_TRY(launch(k_scan_offsets, dim3(job_count), dim3(scan_block_threads), stream, p, device_jobs));
+    if (offset_tables)
+        JLS_TRY(launch(k_write_offset_table, dim3((p.interval_count + 1 + 255) / 256, job_count), dim3(256), stream, p, device_jobs));
     const dim3 gather_grid((p.interval_count + gather_block_threads / 32 - 1) / (gather_block_threads / 32), job_count);
     JLS_TRY(launch(k_gather, gather_grid, dim3(gather_block_threads), stream, p, device_jobs, slot_bytes));
     return cudaSuccess;
@@ -1131,22 +1265,31 @@ cudaError_t launch_encode(const CodecParams& p, const ScanJob* device_jobs, uint
 
 cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint32_t job_count, size_t max_stream_bytes,
                           uint32_t* block_counts, uint32_t* marker_totals, uint8_t* marker_codes, cudaStream_t stream,
-                          cudaEvent_t* coder_events, bool rows_word_aligned)
+                          cudaEvent_t* coder_events, bool rows_word_aligned, bool offset_tables)
 {
     const uint32_t blocks_per_job = static_cast<uint32_t>(marker_blocks_for(max_stream_bytes));
     JLS_TRY(launch(k_init_status, dim3((job_count + 127) / 128), dim3(128), stream, device_jobs, job_count));
     JLS_TRY(launch(k_init_decode_tables, dim3((2 * p.interval_count + 255) / 256, job_count), dim3(256), stream, p,
                    device_jobs));
-    uint16_t* chunk_masks =
-        reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(block_counts) + marker_counts_bytes(job_count, blocks_per_job));
-    const uint32_t marker_grid = (blocks_per_job + marker_sections - 1) / marker_sections;
-    JLS_TRY(launch(k_marker_count, dim3(marker_grid, job_count), dim3(marker_block_threads), stream, device_jobs,
-                   block_counts, blocks_per_job, chunk_masks));
-    JLS_TRY(launch(k_marker_scan, dim3(job_count), dim3(scan_block_threads), stream, block_counts, blocks_per_job,
-                   marker_totals));
-    JLS_TRY(launch(k_marker_write, dim3(marker_grid, job_count), dim3(marker_block_threads), stream, p, device_jobs,
-                   static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes,
-                   static_cast<const uint16_t*>(chunk_masks)));
+    if (offset_tables)
+    {
+        // every job carries a side table of interval offsets: it is checked against the stream and used instead of the search
+        JLS_TRY(launch(k_offsets_from_table, dim3((p.interval_count + 255) / 256, job_count), dim3(256), stream, p, device_jobs,
+                       marker_totals, marker_codes));
+    }
+    else
+    {
+        uint16_t* chunk_masks =
+            reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(block_counts) + marker_counts_bytes(job_count, blocks_per_job));
+        const uint32_t marker_grid = (blocks_per_job + marker_sections - 1) / marker_sections;
+        JLS_TRY(launch(k_marker_count, dim3(marker_grid, job_count), dim3(marker_block_threads), stream, device_jobs,
+                       block_counts, blocks_per_job, chunk_masks));
+        JLS_TRY(launch(k_marker_scan, dim3(job_count), dim3(scan_block_threads), stream, block_counts, blocks_per_job,
+                       marker_totals));
+        JLS_TRY(launch(k_marker_write, dim3(marker_grid, job_count), dim3(marker_block_threads), stream, p, device_jobs,
+                       static_cast<const uint32_t*>(block_counts), blocks_per_job, marker_codes,
+                       static_cast<const uint16_t*>(chunk_masks)));
+    }
 
     const bool lossless = p.near == 0;
     if (coder_events)
@@ -1161,9 +1304,9 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
     {
         const dim3 grid((p.interval_count + general_block_threads - 1) / general_block_threads, job_count);
         if (lossless)
-            JLS_TRY(launch(k_decode_general<true>, grid, dim3(general_block_threads), stream, p, device_jobs));
+            JLS_TRY(launch_general(k_decode_general<true>, grid, p, stream, p, device_jobs));
         else
-            JLS_TRY(launch(k_decode_general<false>, grid, dim3(general_block_threads), stream, p, device_jobs));
+            JLS_TRY(launch_general(k_decode_general<false>, grid, p, stream, p, device_jobs));
     }
     if (coder_events)
         JLS_TRY(cudaEventRecord(coder_events[1], stream));
@@ -1173,10 +1316,10 @@ cudaError_t launch_decode(const CodecParams& p, const ScanJob* device_jobs, uint
 }
 
 cudaError_t launch_wrap_frames(const ScanJob* device_jobs, const uint8_t* device_header, uint32_t header_size,
-                               uint32_t job_count, cudaStream_t stream)
+                               uint32_t job_count, cudaStream_t stream, int parts)
 {
     return launch(k_wrap_frames, dim3((job_count + 3) / 4), dim3(128), stream, device_jobs, device_header, header_size,
-                  job_count);
+                  job_count, parts);
 }
 
 cudaError_t launch_copy_prefixes(const uint8_t* const* device_streams, const size_t* device_sizes, uint8_t* device_prefixes,

@@ -39,7 +39,7 @@ __device__ __forceinline__ void cp_async_wait()
 // base that advances by `rows` rows.  Written as 24 individual steps, each with its own distance to the next, ptxas hoisted
 // all 24 distances out of the tile loop: 120-128 registers for three-component pixels against 64-72 for the others, and
 // 16 resident warps per SM instead of 28.
-template<int TW>
+template<int TW, int SW = TW + 1>
 struct TileWalk
 {
     static_assert(TW == 8 || TW == 12 || TW == 16 || TW == 24, "tiles are 32, 48, 64 or 96 bytes wide");
@@ -58,14 +58,14 @@ struct TileWalk
             const uint32_t index = static_cast<uint32_t>(j) * 32U + lane;
             const uint32_t r = index / TW, w = index % TW;
             global_offset[j] = r * stride + w * 4U;
-            shared_offset[j] = (r * (TW + 1) + w) * 4U;
+            shared_offset[j] = (r * SW + w) * 4U;
         }
     }
 };
 
 // Starts the copy of tile `tile_index` (TW words of each of the warp's 32 lines) into `tile` ([32][TW + 1] words).
 // Lines past `last_line` repeat the last line (never coded); words past the end of a row are zero-filled.
-template<int TW>
+template<int TW, int SW = TW + 1>
 __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* pixels, size_t stride, uint32_t first_line,
                                                 uint32_t last_line, int32_t row_bytes, int32_t tile_index, uint32_t lane)
 {
@@ -74,7 +74,7 @@ __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* p
         // A whole tile (all 32 lines exist, the row does not end inside it): a base per group of rows and the lane's
         // offsets inside a group, no bounds to test.  The general form below costs ~25 instructions per step for index
         // arithmetic (profiles/r1_notes.md), this one 4.
-        const TileWalk<TW> walk(lane, static_cast<uint32_t>(stride));
+        const TileWalk<TW, SW> walk(lane, static_cast<uint32_t>(stride));
         const uint8_t* source = pixels + static_cast<size_t>(first_line) * stride + tile_index * (TW * 4);
         unsigned destination = static_cast<unsigned>(__cvta_generic_to_shared(tile));
 #pragma unroll
@@ -86,7 +86,7 @@ __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* p
                              "l"(source + walk.global_offset[j])
                              : "memory");
             source += TileWalk<TW>::rows * stride;
-            destination += TileWalk<TW>::rows * (TW + 1) * 4U;
+            destination += TileWalk<TW>::rows * SW * 4U;
         }
         cp_async_commit();
         return;
@@ -101,9 +101,44 @@ __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* p
         const bool inside = byte < row_bytes;
         const uint32_t line = min(first_line + r, last_line);
         const uint8_t* source = pixels + static_cast<size_t>(line) * stride + (inside ? byte : 0);
-        cp_async_4(tile + r * (TW + 1) + w, source, inside ? 4 : 0);
+        cp_async_4(tile + r * SW + w, source, inside ? 4 : 0);
     }
     cp_async_commit();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A/B variant (JLS_TILE_LOAD_BULK, off by default): the same tile through the TMA unit's bulk copies, one row per lane
+// (cp.async.bulk.shared.global, SASS UBLKCP) with an mbarrier that counts the bytes.  Two things speak against it, and the
+// measurement agrees (profiles/r2_notes.md): a bulk copy takes its addresses from uniform registers, so 32 lanes with 32 row
+// addresses run a 32-trip ELECT / R2UR / UBLKCP loop (7 issue slots per row, against 16 LDGSTS per lane for the whole tile),
+// and its destination must be 16-byte aligned, so rows cannot be padded to an odd word count: the per-lane walk along a row
+// then meets 4-way bank conflicts.  A 2-D tensor map (one UTMALDG per tile) has the same alignment constraint and needs a
+// descriptor per frame from the driver API.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbarrier_init(uint32_t barrier, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbarrier_wait(uint32_t barrier, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(barrier),
+                 "r"(parity)
+                 : "memory");
+}
+
+// Row r of the warp's tile -> tile + r * row_stride_bytes (a multiple of 16); every lane arrives on the barrier (count 32)
+// with the bytes of its own row.  Whole tiles only (the caller falls back to tile_load_async at the edges).
+template<int TW>
+__device__ __forceinline__ void tile_load_bulk(uint32_t tile_shared, uint32_t row_stride_bytes, uint32_t barrier, const uint8_t* pixels,
+                                               size_t stride, uint32_t first_line, int32_t tile_index, uint32_t lane)
+{
+    const uint8_t* source = pixels + static_cast<size_t>(first_line + lane) * stride + tile_index * (TW * 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "n"(TW * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tile_shared + lane * row_stride_bytes),
+                 "l"(source), "n"(TW * 4), "r"(barrier)
+                 : "memory");
 }
 
 // Writes tile `tile_index` back: row r goes to line first_line + r if bit r of `row_mask` is set.

@@ -205,3 +205,147 @@ def decode_frame_split(stream, decode_strip, dist=None, line_axis=0):
     strips = [None] * world
     dist.all_gather_object(strips, lines)
     return np.concatenate([s for s in strips if s is not None], axis=line_axis)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same split with everything on the devices: strips are coded by charlsx_batch_* from / into CUDA tensors, their
+# entropy-coded segments travel between the GPUs with NCCL (all_gather over NVLink) and are joined on the device; no sample
+# and no stream byte visits the host (only the few header bytes the host has to parse).  Decoding uses the side table of
+# interval offsets in the stream's header (APP11 "JLS-OFFT", include/charls_b200.h): a rank reads where its lines start
+# and end instead of searching the whole stream for restart markers, and fetches only those bytes.
+# ---------------------------------------------------------------------------------------------------------------------
+def _header_and_scan_offset(prefix: bytes):
+    """(bytes in front of the SOS segment, SOS segment) of a single-scan stream whose first bytes are `prefix`."""
+    segments = _segments(prefix)
+    sos_start, sos_end = segments[-1][1], segments[-1][2]
+    return prefix[:sos_start], prefix[sos_start:sos_end]
+
+
+def _without_offset_table(header: bytes) -> bytes:
+    out, position = bytearray(header[:2]), 2
+    for marker, start, end in _segments(header + b"\xff\xda\x00\x02")[:-1]:
+        if not (marker == 0xEB and header[start + 4 : start + 12] == b"JLS-OFFT"):
+            out += header[start:end]
+        position = end
+    return bytes(out)
+
+
+def encode_frame_split_device(frame, make_codec, dist=None):
+    """`frame`: CUDA tensor [H, W] or [H, W, C] (the whole frame on every rank; a rank only reads its own lines).
+    `make_codec(height) -> charls_b200.batch.BatchCodec` for a strip of that many lines (restart interval 1, no offset table).
+    Returns (stream as a CUDA uint8 tensor, size) on every rank: byte for byte what one GPU writes for the whole frame."""
+    import torch
+
+    height = frame.shape[0]
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    device = frame.device
+    heights = [len(strip_range(height, world, r)) for r in range(world)]
+    lines = strip_range(height, world, rank)
+    payload = torch.empty(0, dtype=torch.uint8, device=device)
+    header = sos = b""
+    if len(lines):
+        codec = make_codec(len(lines))
+        strip = frame[lines.start : lines.stop].unsqueeze(0).contiguous()
+        streams = torch.empty((1, codec.stream_capacity), dtype=torch.uint8, device=device)
+        (size,) = codec.encode(strip, streams)
+        header, sos = _header_and_scan_offset(streams[0, :1024].cpu().numpy().tobytes())
+        begin = len(header) + len(sos)
+        payload = streams[0, begin : size - 2]  # without EOI
+        codec.close()
+    sizes = torch.tensor([payload.numel()], dtype=torch.int64, device=device)
+    if world > 1:
+        all_sizes = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(all_sizes, sizes)
+        longest = int(all_sizes.max().item())
+        padded = torch.zeros(longest, dtype=torch.uint8, device=device)
+        padded[: payload.numel()] = payload
+        gathered = torch.empty((world, longest), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(gathered, padded)  # NCCL: the strips' bytes go GPU to GPU
+        all_sizes = all_sizes.tolist()
+        headers = [None] * world
+        dist.all_gather_object(headers, (header, sos))  # a few dozen bytes of marker segments
+        header, sos = next(h for h, n in zip(headers, heights) if n)
+        pieces = [gathered[r, : all_sizes[r]] for r in range(world)]
+    else:
+        pieces = [payload]
+    front = torch.frombuffer(bytearray(_with_height(header, height) + sos), dtype=torch.uint8).to(device)
+    parts, done = [front], 0
+    for r in range(world):
+        if heights[r] == 0:
+            continue
+        if done:
+            parts.append(torch.tensor([0xFF, 0xD0 + (done - 1) % 8], dtype=torch.uint8, device=device))
+        parts.append(pieces[r])
+        done += heights[r]
+    parts.append(torch.tensor([0xFF, 0xD9], dtype=torch.uint8, device=device))
+    stream = torch.cat(parts)
+    return stream, int(stream.numel())
+
+
+def decode_frame_split_device(stream, size, make_codec, dist=None):
+    """`stream`: CUDA uint8 tensor with a single-scan restart-interval-1 stream that carries the side table of interval
+    offsets (every rank has it, e.g. from a broadcast; a rank reads only its strip's bytes).  `make_codec(height)` as above.
+    Returns the whole frame as a CUDA tensor on every rank ([H, row samples...] as the codec shapes it)."""
+    import struct
+
+    import torch
+
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    device = stream.device
+    # the marker segments in front of the scan: SOF55 (height) and the table; the table is at most ~4 bytes per line
+    prefix = stream[: min(size, 1 << 16)].cpu().numpy().tobytes()
+    height = None
+    for marker, start, end in _segments_lenient(prefix):
+        if marker == 0xF7:
+            height = int.from_bytes(prefix[start + 5 : start + 7], "big")
+    prefix = stream[: min(size, 1024 + 4 * (height + 1) + 64 * ((height + 1) // 16377 + 1))].cpu().numpy().tobytes()
+    header, sos = _header_and_scan_offset(prefix)
+    entries = []
+    for marker, start, end in _segments(prefix)[:-1]:
+        if marker == 0xEB and prefix[start + 4 : start + 12] == b"JLS-OFFT":
+            first, count, total = struct.unpack(">III", prefix[start + 14 : start + 26])
+            entries += list(struct.unpack(f">{count}I", prefix[start + 26 : end]))
+    if len(entries) != height + 1:
+        raise ValueError("the stream carries no complete side table of interval offsets")
+    scan_begin = len(header) + len(sos)
+    lines = strip_range(height, world, rank)
+    heights = [len(strip_range(height, world, r)) for r in range(world)]
+    decoded = None
+    if len(lines):
+        begin = scan_begin + entries[lines.start]
+        end = scan_begin + entries[lines.stop] - (2 if lines.stop != height else 0)  # without the restart marker in front of the next strip
+        front = torch.frombuffer(bytearray(_with_height(_without_offset_table(header), len(lines)) + sos), dtype=torch.uint8).to(device)
+        strip_stream = torch.cat([front, stream[begin:end], torch.tensor([0xFF, 0xD9], dtype=torch.uint8, device=device)])
+        codec = make_codec(len(lines))
+        out = codec.decode_new(strip_stream.unsqueeze(0), [int(strip_stream.numel())])
+        decoded = out[0]
+        codec.close()
+    if world == 1:
+        return decoded
+    longest = max(heights)
+    row_shape = None
+    shapes = [None] * world
+    dist.all_gather_object(shapes, None if decoded is None else (tuple(decoded.shape[1:]), str(decoded.dtype)))
+    row_shape, dtype_name = next(s for s in shapes if s is not None)
+    dtype = getattr(torch, dtype_name.split(".")[-1])
+    padded = torch.zeros((longest,) + row_shape, dtype=dtype, device=device)
+    if decoded is not None:
+        padded[: decoded.shape[0]] = decoded
+    gathered = torch.empty((world, longest) + row_shape, dtype=dtype, device=device)
+    dist.all_gather_into_tensor(gathered, padded)  # NCCL: decoded strips GPU to GPU
+    return torch.cat([gathered[r, : heights[r]] for r in range(world) if heights[r]])
+
+
+def _segments_lenient(prefix: bytes):
+    """Like _segments, but stops quietly where the prefix ends (the table may reach beyond it)."""
+    position, out = 2, []
+    while position + 4 <= len(prefix) and prefix[position] == 0xFF:
+        marker = prefix[position + 1]
+        length = int.from_bytes(prefix[position + 2 : position + 4], "big")
+        out.append((marker, position, position + 2 + length))
+        position += 2 + length
+        if marker == 0xDA:
+            break
+    return out

@@ -357,6 +357,16 @@ CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_decoder_decode_to_buffer_begin
                                                                                  uint32_t stride) CHARLS_B200_NOEXCEPT;
 CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_decoder_decode_end(charls_jpegls_decoder* decoder) CHARLS_B200_NOEXCEPT;
 
+/* Side table of interval offsets (extension).  With it the encoder writes, in front of every scan's SOS, one or more
+ * APP11 segments ("JLS-OFFT", charls_b200/csrc/jls_common.h) that list where every restart interval starts.  The reference --
+ * like every other JPEG-LS decoder -- treats them as application data and skips them (reference
+ * src/jpeg_stream_reader.cpp:442-457); this library's decoders use the table instead of searching the stream for restart
+ * markers (and decode as if there were none when the stream does not agree with it), and a rank that decodes only some
+ * lines of a frame knows which bytes it needs.  Off by default on the charls_* objects (their output then differs from a
+ * plain DRI stream by nothing); requires a restart interval. */
+CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_encoder_set_offset_table(charls_jpegls_encoder* encoder,
+                                                                           int32_t enabled) CHARLS_B200_NOEXCEPT;
+
 typedef struct charlsx_batch_image
 {
     void* pixels;           /* device: samples of the frame (encode: input, decode: output), 16-byte aligned */
@@ -375,8 +385,12 @@ typedef struct charlsx_batch_params
     charls_color_transformation color_transformation;
     uint32_t restart_interval; /* encode: interval to write (1 = per line); decode: ignored (read from each stream) */
     uint32_t stride;           /* bytes between lines of `pixels`, 0 = tightly packed */
-    uint32_t reserved;
+    uint32_t flags;            /* CHARLSX_BATCH_* */
 } charlsx_batch_params;
+
+/* encode: write the side table of interval offsets (see charlsx_jpegls_encoder_set_offset_table); decode: the streams may
+ * carry one (the headers are then read far enough to find it; streams without a table decode as always) */
+#define CHARLSX_BATCH_OFFSET_TABLE 1U
 
 typedef struct charlsx_batch charlsx_batch;
 

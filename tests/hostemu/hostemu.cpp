@@ -118,7 +118,9 @@ int64_t hostemu_encode_scan(const CodecParams* pp, const uint8_t* pixels, size_t
         }
         else
         {
-            r = lossless ? encode_interval_general<true>(p, job, i, slot_bytes) : encode_interval_general<false>(p, job, i, slot_bytes);
+            std::vector<RegularContext> general(general_context_count);
+            r = lossless ? encode_interval_general<true>(p, job, i, slot_bytes, general.data())
+                         : encode_interval_general<false>(p, job, i, slot_bytes, general.data());
         }
         interval_bytes[i] = r.bytes;
         if (r.errc != err_none)
@@ -214,7 +216,8 @@ int64_t hostemu_decode_scan(const CodecParams* pp, const uint8_t* stream, size_t
         }
         else
         {
-            r = lossless ? decode_interval_general<true>(p, job, i) : decode_interval_general<false>(p, job, i);
+            std::vector<RegularContext> general(general_context_count);
+            r = lossless ? decode_interval_general<true>(p, job, i, general.data()) : decode_interval_general<false>(p, job, i, general.data());
         }
         if (r.errc != err_none)
             report(i, r.errc);

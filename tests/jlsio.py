@@ -138,3 +138,69 @@ def write_stream(
         out += _seg(0xDA, sos) + payload
     out += b"\xff\xd9"
     return bytes(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Side table of interval offsets (extension, charls_b200/csrc/jls_common.h): APP11 "JLS-OFFT" segments in front of SOS
+# ---------------------------------------------------------------------------------------------------------------------
+OFFSET_TABLE_ID = b"JLS-OFFT"
+OFFSET_TABLE_ENTRIES_PER_SEGMENT = (65533 - 22) // 4
+
+
+def interval_starts(data: bytes) -> list:
+    """Offsets of the interval starts of one scan's entropy-coded bytes plus their total length: what the table lists."""
+    starts, pos = [0], 0
+    while True:
+        i = data.find(b"\xff", pos)
+        if i < 0 or i + 1 >= len(data):
+            break
+        if 0xD0 <= data[i + 1] <= 0xD7:
+            starts.append(i + 2)
+            pos = i + 2
+        else:
+            pos = i + 1
+    return starts + [len(data)]
+
+
+def offset_table_segments(entries: list) -> bytes:
+    out = bytearray()
+    total = len(entries)
+    for first in range(0, total, OFFSET_TABLE_ENTRIES_PER_SEGMENT):
+        part = entries[first : first + OFFSET_TABLE_ENTRIES_PER_SEGMENT]
+        payload = OFFSET_TABLE_ID + bytes([1, 0]) + struct.pack(">III", first, len(part), total) + b"".join(struct.pack(">I", e) for e in part)
+        out += _seg(0xEB, payload)
+    return bytes(out)
+
+
+def read_offset_tables(stream: bytes) -> list:
+    """The tables of a stream, one list of entries per scan that has one (segments in order)."""
+    tables, current = [], []
+    for marker, _, payload in parse(stream).segments:
+        if marker == 0xEB and payload[:8] == OFFSET_TABLE_ID:
+            first, count, total = struct.unpack(">III", payload[10:22])
+            assert first == len(current) and len(payload) == 22 + 4 * count
+            current += list(struct.unpack(f">{count}I", payload[22:]))
+            if len(current) == total:
+                tables.append(current)
+                current = []
+    return tables
+
+
+def with_offset_table(stream: bytes, entries: list | None = None) -> bytes:
+    """The single-scan stream with a side table in front of its SOS (entries: default = the true interval starts)."""
+    s = parse(stream)
+    assert len(s.scans) == 1
+    scan = s.scans[0]
+    sos = next(off for marker, off, _ in s.segments if marker == 0xDA)
+    if entries is None:
+        entries = interval_starts(stream[scan.data_offset : scan.data_end])
+    return stream[:sos] + offset_table_segments(entries) + stream[sos:]
+
+
+def without_offset_table(stream: bytes) -> bytes:
+    out, pos = bytearray(), 0
+    for marker, off, payload in parse(stream).segments:
+        if marker == 0xEB and payload[:8] == OFFSET_TABLE_ID:
+            out += stream[pos:off]
+            pos = off + 4 + len(payload)
+    return bytes(out + stream[pos:])

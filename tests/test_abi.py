@@ -110,6 +110,30 @@ def test_estimated_destination_size_covers_narrow_tall_images(product, oracle):
         assert len(want) <= enc.estimated_destination_size(), (w, h, bits, cc, len(want), enc.estimated_destination_size())
 
 
+def test_offset_table_segments_are_application_data_to_the_reference(product, reference, oracle):
+    """The side table of interval offsets (APP11 "JLS-OFFT", extension): both libraries read the same header from a stream
+    that carries one, both report the segment to an application-data handler, and the reference decodes the stream to the
+    same samples as the stream without it (no GPU needed for any of this)."""
+    import numpy as np
+
+    from tests.support import s_mixed
+
+    for img, bits, ri in ((s_mixed(40, 64, 8, seed=3), 8, 1), (s_mixed(23, 31, 12, seed=4), 12, 4)):
+        plain = oracle.encode_image(img, bits, ri=ri)
+        tabled = jlsio.with_offset_table(plain)
+        assert jlsio.without_offset_table(tabled) == plain and len(tabled) > len(plain)
+        assert header_summary(product, tabled) == header_summary(reference, tabled) == header_summary(reference, plain)
+        want, _, _ = codec.decode(plain, lib=reference)
+        got, _, _ = codec.decode(tabled, lib=reference)
+        assert np.array_equal(got, want)
+        for lib in (product, reference):
+            seen = []
+            with codec.JpegLSDecoder(lib) as dec:
+                dec.at_application_data(lambda app_id, data, size, ctx: seen.append((app_id, C.string_at(data, 8))) or 0)
+                dec.source(tabled).read_header()
+            assert seen == [(11, b"JLS-OFFT")]
+
+
 def header_summary(lib, stream):
     """Everything read_header exposes, or the error code."""
     try:

@@ -322,6 +322,96 @@ def test_damaged_walk_against_the_reference(product, oracle):
     assert extra == damaged_walk.EXPECTED_ACCEPTED_THOUGH_REFERENCE_REJECTS
 
 
+def test_offset_table_written_and_used(product, oracle):
+    """Side table of interval offsets (APP11 "JLS-OFFT"): the encoder's entries are the true interval starts, the scan bytes
+    do not change, the reference decodes the stream (it skips the segment), and our decoder -- which now skips the marker
+    search -- returns the same samples; several segments for tall images; planar frames carry one table per scan."""
+    from charls_b200.codec import JpegLSEncoder
+
+    cases = [(s_mixed(70, 200, 8, seed=1), 8, 1, 0, 1), (s_smooth(33, 64, 16, 3, seed=9, layout="interleaved"), 16, 3, 2, 1),
+             (s_noise(41, 52, 12, seed=3), 12, 1, 0, 3), (s_mixed(24, 40, 8, 3, seed=5, layout="planar"), 8, 3, 0, 1),
+             (s_mixed(17000, 8, 8, seed=2), 8, 1, 0, 1)]
+    for img, bits, cc, ilv, ri in cases:
+        h, w = (img.shape[1], img.shape[2]) if (cc > 1 and ilv == 0) else (img.shape[0], img.shape[1])
+        with JpegLSEncoder(product) as enc:
+            enc.frame_info(w, h, bits, cc).interleave_mode(ilv).restart_interval(ri).offset_table(True)
+            dst = np.zeros(enc.estimated_destination_size(), np.uint8)
+            enc.destination(dst)
+            stream = dst[: enc.encode(img)].tobytes()
+        plain = encode(product, img, bits, interleave_mode=ilv, restart_interval=ri)
+        assert jlsio.without_offset_table(stream) == plain
+        parsed = jlsio.parse(stream)
+        tables = jlsio.read_offset_tables(stream)
+        assert len(tables) == len(parsed.scans)
+        for table, scan in zip(tables, parsed.scans):
+            assert table == jlsio.interval_starts(stream[scan.data_offset : scan.data_end])
+        got, _, _ = codec.decode(stream, lib=product)
+        assert got.tobytes() == np.ascontiguousarray(img).tobytes()
+        if have_reference_build():
+            want, _, _ = codec.decode(stream, lib=reference_library())
+            assert np.array_equal(got, want)
+
+
+def test_offset_table_is_checked_before_it_is_believed(product, oracle):
+    """A table that does not agree with the stream changes nothing: the answer -- samples or error code -- is the one the
+    stream gives without a table.  Wrong entries, entries that skip a marker, a marker hidden inside an interval, and the
+    whole damaged walk with the undamaged stream's table in front."""
+    from tests import damaged_walk
+
+    def outcome(stream):
+        try:
+            px, _, _ = codec.decode(stream, lib=product)
+            return 0, px.tobytes()
+        except CharlsError as e:
+            return e.errc, b""
+
+    img = s_mixed(40, 120, 8, seed=4)
+    good = oracle.encode_image(img, 8, ri=1)
+    scan = jlsio.parse(good).scans[0]
+    starts = jlsio.interval_starts(good[scan.data_offset : scan.data_end])
+    assert outcome(jlsio.with_offset_table(good)) == outcome(good) == (0, img.tobytes())
+    for mutate in (lambda e: [x + (1 if i == 7 else 0) for i, x in enumerate(e)],  # one entry off by one
+                   lambda e: e[:5] + [e[6]] + e[6:],                                # an interval skipped
+                   lambda e: [0] * len(e), lambda e: list(reversed(e)), lambda e: e[:-1] + [e[-1] + 400]):
+        assert outcome(jlsio.with_offset_table(good, mutate(starts))) == (0, img.tobytes())
+    # a restart marker where none belongs: the table (made for the stream as it is) points past it, the search does not
+    data = bytearray(good)
+    data[scan.data_offset + starts[9] + 3 : scan.data_offset + starts[9] + 3] = b"\xff\xd3"
+    damaged = bytes(data)
+    shifted = [x + (2 if i > 9 else 0) for i, x in enumerate(starts)]
+    assert outcome(jlsio.with_offset_table(damaged, shifted)) == outcome(damaged)
+    assert outcome(damaged)[0] != 0
+    # the damaged walk: every damaged stream with the table of the undamaged one
+    compared = 0
+    for key, stream, data, walk_img, sp in damaged_walk.damaged_streams(oracle):
+        if sp.restart_interval == 0 or key[-1] % 4 != 0:
+            continue
+        good_scan = oracle.encode_scan(sp, walk_img)
+        tabled = jlsio.with_offset_table(stream, jlsio.interval_starts(good_scan))
+        assert outcome(tabled) == outcome(stream), key
+        compared += 1
+    assert compared > 200
+
+
+def test_one_frame_across_gpus_on_the_devices(product):
+    """tools/split_frame_check.py: strips coded on the device, joined on the device (NCCL between ranks), decoded strip by
+    strip through the side table of interval offsets.  One process here; with two or more GPUs also two ranks under torchrun."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tools", "split_frame_check.py")
+    one = subprocess.run([sys.executable, script, "2056", "1024"], capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stdout + one.stderr
+    if torch.cuda.device_count() >= 2:
+        two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                              "127.0.0.1", "--master-port", "29571", script, "2056", "1024"], capture_output=True, text=True, timeout=900)
+        assert two.returncode == 0, two.stdout + two.stderr
+
+
 def test_instances_on_threads(product, oracle):
     """Distinct encoder / decoder instances are independent (reference: undocumented but de facto)."""
     images = [s_mixed(50, 90, 8, seed=i) for i in range(8)]
@@ -369,6 +459,46 @@ def test_batch_interface(product, oracle):
         for i in range(n):
             expected, _ = oracle.decode_image(host[i, : sizes[i]].tobytes())
             assert np.array_equal(got[i], expected), (w, h, bits, i)
+        bc.close()
+    # with the side table of interval offsets: same scan bytes, true entries, decode through the table, a frame whose table
+    # is wrong or missing makes no difference, host-resident batches too
+    for (w, h, bits, cc, ilv, xf) in ((96, 40, 8, 1, 0, 0), (33, 17, 16, 3, 2, 1)):
+        n = 6
+        frames_np = [s_mixed(h, w, bits, cc, seed=40 + i, layout="interleaved") for i in range(n)]
+        arr = np.stack(frames_np)
+        t = torch.from_numpy(arr.view(np.int16) if bits > 8 else arr).to(device)
+        bc = BatchCodec(w, h, bits, cc, interleave_mode=ilv, color_transformation=xf, offset_table=True, lib=product)
+        streams = torch.zeros((n, bc.stream_capacity), dtype=torch.uint8, device=device)
+        sizes = bc.encode(t, streams)
+        host = streams.cpu().numpy()
+        for i in range(n):
+            stream = host[i, : sizes[i]].tobytes()
+            assert jlsio.without_offset_table(stream) == encode(product, frames_np[i], bits, interleave_mode=ilv, color_transformation=xf)
+            scan = jlsio.parse(stream).scans[0]
+            assert jlsio.read_offset_tables(stream) == [jlsio.interval_starts(stream[scan.data_offset : scan.data_end])]
+        out = torch.zeros_like(t)
+        bc.decode(streams, sizes, out)
+        assert torch.equal(out, t)
+        # frame 2: table entries zeroed; frame 4: no table at all (shorter stream) -- the batch falls back to the marker search
+        mixed = host.copy()
+        sizes2 = list(sizes)
+        stream = host[2, : sizes[2]].tobytes()
+        first_entry = stream.find(jlsio.OFFSET_TABLE_ID) + 22
+        mixed[2, first_entry + 4 : first_entry + 44] = 0
+        plain = jlsio.without_offset_table(host[4, : sizes[4]].tobytes())
+        mixed[4, : len(plain)] = np.frombuffer(plain, np.uint8)
+        sizes2[4] = len(plain)
+        out.zero_()
+        bc.decode(torch.from_numpy(mixed).to(device), sizes2, out)
+        assert torch.equal(out, t)
+        pinned_in = [t[i].cpu().pin_memory() for i in range(n)]
+        pinned_streams = [torch.zeros(bc.stream_capacity, dtype=torch.uint8).pin_memory() for _ in range(n)]
+        pinned_out = [torch.zeros_like(pinned_in[i]).pin_memory() for i in range(n)]
+        host_sizes = bc.encode_host(pinned_in, pinned_streams)
+        assert list(host_sizes) == list(sizes)
+        assert all(pinned_streams[i][: sizes[i]].numpy().tobytes() == host[i, : sizes[i]].tobytes() for i in range(n))
+        bc.decode_host(pinned_streams, host_sizes, pinned_out)
+        assert all(torch.equal(pinned_out[i], pinned_in[i]) for i in range(n))
         bc.close()
     # a stream that is too small is reported per frame, the others are still coded
     bc = BatchCodec(64, 64, 8, lib=product)
