@@ -651,6 +651,40 @@ def run_gpu_arm(args):
         e2e["host_batch_value"] = world * passes * n * w * h / float(tb.item()) / 1e6
         e2e["host_batch_api"] = "charlsx_batch_encode_host, then charlsx_batch_decode_host (extension), one host thread per GPU, same pinned buffers"
 
+        # ---- both PCIe directions at once: one thread encodes half of the frames while a second one decodes the streams of the
+        # other half (two batch objects), then the halves swap roles; a round trip still is one encode plus one decode of a frame
+        if n >= 2:
+            codec_b = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf,
+                                 restart_interval=args.restart_interval, offset_table=not args.no_offset_table, lib=lib)
+            lower = [i % (n // 2) for i in range(passes * (n // 2))]            # buffers 0 .. n/2-1, each `passes` times
+            upper = [n // 2 + i % (n - n // 2) for i in range(passes * (n - n // 2))]  # buffers n/2 .. n-1: the halves share nothing
+            first = ([frames_host[i] for i in lower], [streams_host[i] for i in lower], [out_host[i] for i in lower], [batch_sizes[i] for i in lower])
+            second = ([frames_host[i] for i in upper], [streams_host[i] for i in upper], [out_host[i] for i in upper], [batch_sizes[i] for i in upper])
+
+            def two_way(encode_side, decode_side):
+                worker = threading.Thread(target=lambda: codec_b.decode_host(decode_side[1], decode_side[3], decode_side[2]))
+                worker.start()
+                codec.encode_host(encode_side[0], encode_side[1])
+                worker.join()
+
+            t_two = 0.0
+            for rep in range(1 + batch_reps):
+                if world > 1 and rep == 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                two_way(first, second)  # streams of `second` are from the previous encode, `first` gets new ones
+                two_way(second, first)
+                if rep >= 1:
+                    t_two += time.perf_counter() - t0
+            if near == 0:
+                assert torch.equal(out_host, frames_host), "two-way host-batch mismatch"
+            tt = torch.tensor([t_two / batch_reps], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e["host_batch_two_way_value"] = world * passes * n * w * h / float(tt.item()) / 1e6
+            e2e["host_batch_two_way_api"] = "charlsx_batch_encode_host of one half of the frames while a second thread runs charlsx_batch_decode_host on the other half's streams"
+            codec_b.close()
+
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_kind = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
@@ -664,7 +698,7 @@ def run_gpu_arm(args):
         del frames, streams, decoded
         torch.cuda.empty_cache()
         for other in others:
-            also[other] = secondary_workload(torch, dist, lib, device, rank, world, other, max(1, args.frames // 2), max(3, args.steps // 4), peak,
+            also[other] = secondary_workload(torch, dist, lib, device, rank, world, other, args.frames, max(3, args.steps // 4), peak,
                                              not args.no_offset_table)
 
     if rank != 0:

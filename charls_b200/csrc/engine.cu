@@ -1092,7 +1092,7 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
     return first_error;
 }
 
-int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, std::vector<uint8_t>& prefixes,
+int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, const uint8_t*& prefixes,
                                   CUstream_st* user_stream)
 {
     JLS_CHECK(prepare());
@@ -1115,8 +1115,7 @@ int32_t Engine::download_prefixes(const BatchFrame* frames, size_t count, uint32
                                   static_cast<uint8_t*>(prefixes_.data), prefix_bytes, static_cast<uint32_t>(count), stream));
     JLS_CUDA(cudaMemcpyAsync(host_prefixes_.data, prefixes_.data, count * prefix_bytes, cudaMemcpyDeviceToHost, stream));
     JLS_CHECK(wait_for(stream));
-    prefixes.assign(static_cast<const uint8_t*>(host_prefixes_.data),
-                    static_cast<const uint8_t*>(host_prefixes_.data) + count * prefix_bytes);
+    prefixes = static_cast<const uint8_t*>(host_prefixes_.data); // parsed where they are (pinned; the next call reuses the buffer)
     return 0;
 }
 

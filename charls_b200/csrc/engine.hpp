@@ -99,7 +99,7 @@ public:
                               size_t stride, const StreamOffsetTable* table = nullptr);
     int32_t decode_batch_host(const CodecParams& p, BatchFrame* frames, size_t count, size_t stride);
     // Downloads the first `prefix_bytes` of every frame's stream (header parsing happens on the host).
-    int32_t download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, std::vector<uint8_t>& prefixes,
+    int32_t download_prefixes(const BatchFrame* frames, size_t count, uint32_t prefix_bytes, const uint8_t*& prefixes,
                               CUstream_st* user_stream);
 
     uint32_t last_kernel_launches() const noexcept { return last_launches_; }

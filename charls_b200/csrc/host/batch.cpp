@@ -179,7 +179,7 @@ charls_jpegls_errc decode_frames(charlsx_batch* batch, const charlsx_batch_param
         // with side tables of interval offsets in the headers, SOS sits behind them: read that much more of every stream
         const uint32_t prefix_bytes =
             header_prefix_bytes + ((bp.flags & CHARLSX_BATCH_OFFSET_TABLE) != 0 ? static_cast<uint32_t>(offset_table_bytes(f.height)) : 0U);
-        std::vector<uint8_t> prefixes;
+        const uint8_t* prefixes = nullptr; // in the engine's pinned staging buffer, valid until its next call
         if (!host_memory)
             check_status(batch->engine.download_prefixes(batch->frames.data(), count, prefix_bytes, prefixes, stream));
 
@@ -193,7 +193,7 @@ charls_jpegls_errc decode_frames(charlsx_batch* batch, const charlsx_batch_param
             const size_t available = frame.stream_capacity < prefix_bytes ? frame.stream_capacity : prefix_bytes;
             const charls_jpegls_errc errc = guarded([&] {
                 StreamReader reader;
-                reader.source(host_memory ? frame.stream : prefixes.data() + i * prefix_bytes, available);
+                reader.source(host_memory ? frame.stream : prefixes + i * prefix_bytes, available);
                 reader.read_header();
                 const charls_frame_info& info = reader.frame_info();
                 // every frame must match the batch description

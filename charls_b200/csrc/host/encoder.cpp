@@ -7,6 +7,7 @@
 #include "abi_support.hpp"
 #include "stream_writer.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 using namespace jls;
@@ -408,7 +409,18 @@ private:
     int32_t interleave_mode_{};
     int32_t color_transformation_{};
     uint32_t encoding_options_{};
-    uint32_t restart_interval_{1}; // one line per restart interval: every line is an independent work item
+    // One line per restart interval: every line is an independent work item.  The reference writes none (and so does this
+    // library with CHARLS_B200_RESTART_INTERVAL=0 or charlsx_jpegls_encoder_set_restart_interval(encoder, 0): byte-identical
+    // output, one CUDA thread per scan).
+    uint32_t restart_interval_{default_restart_interval()};
+    static uint32_t default_restart_interval() noexcept
+    {
+        static const uint32_t value = [] {
+            const char* text = std::getenv("CHARLS_B200_RESTART_INTERVAL");
+            return text && text[0] >= '0' && text[0] <= '9' ? static_cast<uint32_t>(std::strtoul(text, nullptr, 10)) : 1U;
+        }();
+        return value;
+    }
     State state_{State::initial};
     StreamWriter writer_;
     charls_jpegls_pc_parameters user_preset_{};

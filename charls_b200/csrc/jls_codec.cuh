@@ -814,7 +814,7 @@ struct GeneralState
 
 // Scalar line (ILV none and every component line of ILV line); reference src/scan_encoder_impl.hpp:109-144,249-275
 template<bool LOSSLESS>
-JLS_HD_NOINLINE void general_encode_line(const CodecParams& p, GeneralState& s, BitWriter& bw, uint16_t* cur,
+JLS_HD void general_encode_line(const CodecParams& p, GeneralState& s, BitWriter& bw, uint16_t* cur,
                                          const uint16_t* prev)
 {
     // the neighbourhood slides along in registers, see general_decode_line
@@ -881,7 +881,7 @@ JLS_HD_NOINLINE void general_encode_line(const CodecParams& p, GeneralState& s, 
 
 // Sample-interleaved line; reference src/scan_encoder_impl.hpp:147-246,249-310. cur/prev: component c at + c * (width + 2).
 template<bool LOSSLESS>
-JLS_HD_NOINLINE void general_encode_line_multi(const CodecParams& p, GeneralState& s, BitWriter& bw, uint16_t* cur,
+JLS_HD void general_encode_line_multi(const CodecParams& p, GeneralState& s, BitWriter& bw, uint16_t* cur,
                                                const uint16_t* prev)
 {
     const int32_t width = p.width, nc = p.components, ps = width + 2;
@@ -948,7 +948,7 @@ JLS_HD_NOINLINE void general_encode_line_multi(const CodecParams& p, GeneralStat
 
 // reference src/scan_decoder_impl.hpp:132-159,264-281 + src/scan_decoder_core.hpp:83-92
 template<bool LOSSLESS>
-JLS_HD_NOINLINE void general_decode_line(const CodecParams& p, GeneralState& s, BitReader& br, uint16_t* cur,
+JLS_HD void general_decode_line(const CodecParams& p, GeneralState& s, BitReader& br, uint16_t* cur,
                                          const uint16_t* prev)
 {
     // The neighbourhood slides along in registers: Ra is the sample just decoded, Rc and Rb were Rb and Rd one pixel ago,
@@ -1011,7 +1011,7 @@ JLS_HD_NOINLINE void general_decode_line(const CodecParams& p, GeneralState& s, 
 
 // reference src/scan_decoder_impl.hpp:162-261,283-303 + src/scan_decoder_core.hpp:94-100
 template<bool LOSSLESS>
-JLS_HD_NOINLINE void general_decode_line_multi(const CodecParams& p, GeneralState& s, BitReader& br, uint16_t* cur,
+JLS_HD void general_decode_line_multi(const CodecParams& p, GeneralState& s, BitReader& br, uint16_t* cur,
                                                const uint16_t* prev)
 {
     const int32_t width = p.width, nc = p.components, ps = width + 2;
