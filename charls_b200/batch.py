@@ -41,17 +41,30 @@ class BatchCodec:
 
     __del__ = close
 
+    _IMAGE_DTYPE = None
+
     def _images(self, pixels, streams, sizes):
+        """The charlsx_batch_image array of a call, filled column by column through a numpy view of the same memory (a Python
+        loop over 128 frames costs more than the library needs to issue the whole batch)."""
+        import numpy as np
+
+        if BatchCodec._IMAGE_DTYPE is None:
+            BatchCodec._IMAGE_DTYPE = np.dtype([("pixels", "<u8"), ("stream", "<u8"), ("stream_capacity", "<u8"), ("stream_size", "<u8"),
+                                                ("status", "<i4"), ("reserved", "<i4")])
+            assert BatchCodec._IMAGE_DTYPE.itemsize == C.sizeof(BatchImage)
         n = pixels.shape[0]
         images = (BatchImage * n)()
-        pixel_stride = pixels.stride(0) * pixels.element_size()
+        view = np.frombuffer(images, dtype=BatchCodec._IMAGE_DTYPE)
+        index = np.arange(n, dtype=np.uint64)
+        view["pixels"] = pixels.data_ptr() + index * np.uint64(pixels.stride(0) * pixels.element_size())
         stream_stride = streams.stride(0) * streams.element_size()
-        p0, s0 = pixels.data_ptr(), streams.data_ptr()
-        for i in range(n):
-            images[i].pixels = p0 + i * pixel_stride
-            images[i].stream = s0 + i * stream_stride
-            images[i].stream_capacity = stream_stride if sizes is None else int(sizes[i])
+        view["stream"] = streams.data_ptr() + index * np.uint64(stream_stride)
+        view["stream_capacity"] = stream_stride if sizes is None else np.asarray(sizes, dtype=np.uint64)
+        self._last_view = view
         return images
+
+    def _stream_sizes(self, images):
+        return self._last_view["stream_size"].tolist()
 
     @staticmethod
     def _stream_handle(stream):
@@ -66,14 +79,14 @@ class BatchCodec:
         images = self._images(pixels, streams, None)
         errc = self.lib.charlsx_batch_encode(self._h, byref(self.params), images, len(images), self._stream_handle(stream))
         self.lib.check(errc)
-        return [images[i].stream_size for i in range(len(images))]
+        return self._stream_sizes(images)
 
     def decode(self, streams, sizes, pixels, stream=None):
         """streams: CUDA uint8 tensor [N, capacity] holding complete JPEG-LS streams of `sizes` bytes; pixels: output."""
         images = self._images(pixels, streams, sizes)
         errc = self.lib.charlsx_batch_decode(self._h, byref(self.params), images, len(images), self._stream_handle(stream))
         self.lib.check(errc)
-        return [images[i].stream_size for i in range(len(images))]
+        return self._stream_sizes(images)
 
     def decode_new(self, streams, sizes, stream=None):
         """decode() into a new CUDA tensor [N, H, W] or [N, H, W, C] (uint8, or int16 carrying the uint16 bit pattern)."""
