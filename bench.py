@@ -496,6 +496,11 @@ def run_gpu_arm(args):
         b = frames.to(torch.int32) & 0xFFFF if bits > 8 else frames.to(torch.int32)
         assert int((a - b).abs().max()) <= near, "near-lossless bound violated"
 
+    # one stream of the batch and its frame go to the host: the reference decodes it in the cpu_baseline leg (after the timed
+    # regions), so that a bench line is never just our decoder agreeing with our encoder
+    check_stream = streams[0, : sizes[0]].cpu().numpy().tobytes() if rank == 0 else None
+    check_frame = frames[0].cpu().numpy() if rank == 0 else None
+
     launches_before = C.c_uint64()
     lib.check(lib.charlsx_get_kernel_launch_count(C.byref(launches_before)))
     sampler = ClockSampler(local_rank)
@@ -580,6 +585,32 @@ def run_gpu_arm(args):
         value_two_part, _ = measure(threads, inflight)
         comp = sum(e2e_sizes)
 
+        # One image, one thread: what a single synchronous call costs (copy in, kernels, copy out)
+        lat = {"enc": [], "dec": []}
+        fi_one = capi.FrameInfo(w, h, bits, cc)
+        for _ in range(12):
+            e = lib.charls_jpegls_encoder_create()
+            lib.check(lib.charls_jpegls_encoder_set_frame_info(e, C.byref(fi_one)))
+            lib.check(lib.charls_jpegls_encoder_set_near_lossless(e, near))
+            lib.check(lib.charls_jpegls_encoder_set_interleave_mode(e, ilv))
+            lib.check(lib.charls_jpegls_encoder_set_color_transformation(e, xf))
+            lib.check(lib.charls_jpegls_encoder_set_destination_buffer(e, streams_host[0].data_ptr(), streams_host.shape[1]))
+            t0 = time.perf_counter()
+            lib.check(lib.charls_jpegls_encoder_encode_from_buffer(e, frames_host[0].data_ptr(), raw_bytes, 0))
+            lat["enc"].append(time.perf_counter() - t0)
+            one_size = C.c_size_t()
+            lib.check(lib.charls_jpegls_encoder_get_bytes_written(e, C.byref(one_size)))
+            lib.charls_jpegls_encoder_destroy(e)
+            d = lib.charls_jpegls_decoder_create()
+            lib.check(lib.charls_jpegls_decoder_set_source_buffer(d, streams_host[0].data_ptr(), one_size.value))
+            lib.check(lib.charls_jpegls_decoder_read_header(d))
+            t0 = time.perf_counter()
+            lib.check(lib.charls_jpegls_decoder_decode_to_buffer(d, out_host[0].data_ptr(), raw_bytes, 0))
+            lat["dec"].append(time.perf_counter() - t0)
+            lib.charls_jpegls_decoder_destroy(d)
+        one_image_encode_ms = float(np.median(lat["enc"][2:])) * 1e3
+        one_image_decode_ms = float(np.median(lat["dec"][2:])) * 1e3
+
         # What the box can copy: all ranks move the same bytes host->device and device->host at the same time (pinned buffers,
         # two streams, no kernel).  On the multi-GPU boxes of this pool the GPUs share the host's PCIe / memory path
         # (tools/pcie_probe_ranks.py: 96 GB/s both ways for one GPU, 104 for two, 120 for four), so this -- not the codec --
@@ -622,6 +653,7 @@ def run_gpu_arm(args):
             "api": "charls_jpegls_encoder_encode_from_buffer + charls_jpegls_decoder_decode_to_buffer, pinned host buffers",
             "two_part_calls_value": value_two_part, "two_part_calls_host_threads": threads, "two_part_calls_in_flight_per_thread": inflight,
             "two_part_calls_api": "charlsx_jpegls_encoder_encode_from_buffer_begin/_end + charlsx_jpegls_decoder_decode_to_buffer_begin/_end",
+            "one_image_encode_call_ms": one_image_encode_ms, "one_image_decode_call_ms": one_image_decode_ms,
             "box_copy_gbs_each_way": copy_gbs_each_way, "box_copy_ceiling_mpix_s": copy_ceiling,
             "frac_of_box_copy_ceiling": value_one_part / copy_ceiling,
             "box_copy_ceiling_how": "all ranks copy the same pinned buffers up and down at the same time, no kernel (CUDA events, max over ranks)",
@@ -759,6 +791,17 @@ def run_gpu_arm(args):
             reps += 1
         cpu_baseline = {"value": threads * reps * w * h / t / 1e6, "unit": "MPixels/s", "cores": threads, "kind": "reference",
                         "sample": f"{threads} threads x {reps} frames of {args.workload}: unmodified reference encode (no restart markers) + decode"}
+        # the reference as the checker of the GPU arm: it decodes frame 0's stream of the timed batch (side table and all)
+        from charls_b200 import codec as host_codec
+
+        ref_pixels, _, _ = host_codec.decode(check_stream, lib=ref)
+        mine = check_frame.view(np.uint16) if bits > 8 else check_frame
+        if near == 0:
+            agrees = bool(np.array_equal(ref_pixels.reshape(mine.shape), mine))
+        else:
+            agrees = int(np.abs(ref_pixels.reshape(mine.shape).astype(np.int64) - mine.astype(np.int64)).max()) <= near
+        assert agrees, "the reference decodes a stream of the timed batch to something else than its frame"
+        cpu_baseline["reference_decodes_bench_stream"] = agrees
 
     out = {
         "metric": METRIC, "value": value, "unit": "MPixels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

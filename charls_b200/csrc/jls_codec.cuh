@@ -787,6 +787,10 @@ struct GeneralState
     // restart interval per scan only one lane of a warp works, every context access touched a cache line of its own and
     // the 187 KB a warp's contexts then span did not stay in L1 (31 -> ~1 MPix/s per stream, profiles/r2_notes.md).
     RegularContext* contexts;
+    // Optional table of quantize_gradient(d) for d in [-MAXVAL, MAXVAL] at quant_lut[d + MAXVAL] (shared memory in the kernels
+    // for samples of up to 12 bits; the reference's quantization_lut, src/scan_codec.hpp:22-99): one load instead of a chain
+    // of up to eight compares, three times per sample.
+    const int8_t* quant_lut;
     RunContext run_contexts[2];
     int32_t run_index;
     bool bad;
@@ -808,6 +812,11 @@ struct GeneralState
     JLS_HD int32_t context_id(const CodecParams& p, int32_t ra, int32_t rb, int32_t rc, int32_t rd) const
     {
         // reference src/jpegls_algorithm.hpp:165-168
+        if (quant_lut != nullptr)
+        {
+            const int8_t* q = quant_lut + p.maxval;
+            return (q[rd - rb] * 9 + q[rb - rc]) * 9 + q[rc - ra];
+        }
         return (quantize_gradient(p, rd - rb) * 9 + quantize_gradient(p, rb - rc)) * 9 + quantize_gradient(p, rc - ra);
     }
 };

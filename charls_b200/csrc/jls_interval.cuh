@@ -264,7 +264,7 @@ JLS_HD void general_set_edges(uint16_t* cur, uint16_t* prev, int32_t nc, int32_t
 
 template<bool LOSSLESS>
 JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval,
-                                                       size_t slot_bytes, RegularContext* contexts)
+                                                       size_t slot_bytes, RegularContext* contexts, const int8_t* quant_lut = nullptr)
 {
     const int32_t width = p.width, ps = width + 2, nc = p.components;
     const size_t per_interval = static_cast<size_t>(2) * nc * ps;
@@ -274,6 +274,7 @@ JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, con
 
     GeneralState state;
     state.contexts = contexts; // general_context_count entries owned by this thread (shared memory in the kernels)
+    state.quant_lut = quant_lut;
     state.reset(p);
     state.bad = false;
     int32_t run_index[4] = {0, 0, 0, 0};
@@ -330,7 +331,7 @@ JLS_HD_NOINLINE IntervalResult encode_interval_general(const CodecParams& p, con
 
 template<bool LOSSLESS>
 JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, const ScanJob& job, uint32_t interval,
-                                                       RegularContext* contexts)
+                                                       RegularContext* contexts, const int8_t* quant_lut = nullptr)
 {
     IntervalResult result = {err_none, 0};
     const uint64_t begin = job.interval_offset[2 * static_cast<size_t>(interval)];
@@ -351,6 +352,7 @@ JLS_HD_NOINLINE IntervalResult decode_interval_general(const CodecParams& p, con
 
     GeneralState state;
     state.contexts = contexts; // general_context_count entries owned by this thread (shared memory in the kernels)
+    state.quant_lut = quant_lut;
     state.reset(p);
     state.bad = false;
     int32_t run_index[4] = {0, 0, 0, 0};

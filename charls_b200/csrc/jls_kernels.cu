@@ -450,18 +450,44 @@ __global__ void __launch_bounds__(fast_block_threads)
 // General path: one thread per restart interval, full 2-D LOCO-I (365 contexts in local memory).
 // ---------------------------------------------------------------------------------------------------------------------
 // Dynamic shared memory: general_context_count contexts (5840 bytes) per thread that has an interval -- 32 in a full
-// block (one block per SM then), one for scans without restart markers (one interval per scan, one working lane per warp).
+// block (one block per SM then), one for scans without restart markers (one interval per scan, one working lane per warp) --
+// and behind them, for samples of up to 12 bits (general_quant_lut_max_maxval), the gradient quantisation table of the block.
+constexpr int32_t general_quant_lut_max_maxval = 4095;
+
+__host__ __device__ inline size_t general_working_threads(const CodecParams& p)
+{
+    return p.interval_count < static_cast<uint32_t>(general_block_threads) ? p.interval_count : general_block_threads;
+}
+
+__host__ __device__ inline size_t general_quant_lut_bytes(const CodecParams& p)
+{
+    return p.maxval <= general_quant_lut_max_maxval ? (static_cast<size_t>(2 * p.maxval + 1) + 15U) / 16U * 16U : 0U;
+}
+
+// all threads of the block call this before any of them leaves
+__device__ __forceinline__ const int8_t* fill_general_quant_lut(const CodecParams& p, uint8_t* shared)
+{
+    if (general_quant_lut_bytes(p) == 0)
+        return nullptr;
+    int8_t* lut = reinterpret_cast<int8_t*>(shared + general_working_threads(p) * general_context_count * sizeof(RegularContext));
+    for (int32_t i = threadIdx.x; i <= 2 * p.maxval; i += general_block_threads)
+        lut[i] = static_cast<int8_t>(quantize_gradient(p, i - p.maxval));
+    __syncthreads();
+    return lut;
+}
+
 template<bool LOSSLESS>
 __global__ void __launch_bounds__(general_block_threads)
     k_encode_general(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs, size_t slot_bytes)
 {
     extern __shared__ __align__(16) uint8_t general_shared[];
+    const int8_t* quant_lut = fill_general_quant_lut(p, general_shared);
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t interval = blockIdx.x * general_block_threads + threadIdx.x;
     if (interval >= p.interval_count)
         return;
     RegularContext* contexts = reinterpret_cast<RegularContext*>(general_shared) + threadIdx.x * general_context_count;
-    const IntervalResult r = encode_interval_general<LOSSLESS>(p, job, interval, slot_bytes, contexts);
+    const IntervalResult r = encode_interval_general<LOSSLESS>(p, job, interval, slot_bytes, contexts, quant_lut);
     job.interval_bytes[interval] = r.bytes;
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
@@ -472,12 +498,13 @@ __global__ void __launch_bounds__(general_block_threads)
     k_decode_general(const __grid_constant__ CodecParams p, const ScanJob* __restrict__ jobs)
 {
     extern __shared__ __align__(16) uint8_t general_shared[];
+    const int8_t* quant_lut = fill_general_quant_lut(p, general_shared);
     const ScanJob& job = jobs[blockIdx.y];
     const uint32_t interval = blockIdx.x * general_block_threads + threadIdx.x;
     if (interval >= p.interval_count)
         return;
     RegularContext* contexts = reinterpret_cast<RegularContext*>(general_shared) + threadIdx.x * general_context_count;
-    const IntervalResult r = decode_interval_general<LOSSLESS>(p, job, interval, contexts);
+    const IntervalResult r = decode_interval_general<LOSSLESS>(p, job, interval, contexts, quant_lut);
     if (r.errc != err_none)
         report_error(job, interval, r.errc);
 }
@@ -1050,8 +1077,7 @@ cudaError_t launch_with_shared(Kernel kernel, dim3 grid, dim3 block, size_t dyna
 template<typename Kernel, typename... Args>
 cudaError_t launch_general(Kernel kernel, dim3 grid, const CodecParams& p, cudaStream_t stream, Args... args)
 {
-    const size_t working = p.interval_count < static_cast<uint32_t>(general_block_threads) ? p.interval_count : general_block_threads;
-    const size_t bytes = working * general_context_count * sizeof(RegularContext);
+    const size_t bytes = general_working_threads(p) * general_context_count * sizeof(RegularContext) + general_quant_lut_bytes(p);
     if (bytes > 48U * 1024U)
     {
         const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -77,14 +77,24 @@ __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* p
         const TileWalk<TW, SW> walk(lane, static_cast<uint32_t>(stride));
         const uint8_t* source = pixels + static_cast<size_t>(first_line) * stride + tile_index * (TW * 4);
         unsigned destination = static_cast<unsigned>(__cvta_generic_to_shared(tile));
+#if defined(JLS_L2_HINTS) && (JLS_L2_HINTS & 2)
+        uint64_t load_policy;
+        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(load_policy));
+#endif
 #pragma unroll
         for (int g = 0; g < TileWalk<TW>::groups; ++g)
         {
 #pragma unroll
             for (int j = 0; j < TileWalk<TW>::period; ++j)
+#if defined(JLS_L2_HINTS) && (JLS_L2_HINTS & 2)
+                asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(destination + walk.shared_offset[j]),
+                             "l"(source + walk.global_offset[j]), "l"(load_policy)
+                             : "memory");
+#else
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(destination + walk.shared_offset[j]),
                              "l"(source + walk.global_offset[j])
                              : "memory");
+#endif
             source += TileWalk<TW>::rows * stride;
             destination += TileWalk<TW>::rows * SW * 4U;
         }
