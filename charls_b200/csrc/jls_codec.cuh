@@ -100,6 +100,29 @@ JLS_HD uint32_t shr_sat(uint32_t v, uint32_t count)
 #endif
 }
 
+// the same for 64-bit values, count in [0, 64]
+JLS_HD uint64_t shl64_sat(uint64_t v, uint32_t count)
+{
+#if defined(__CUDA_ARCH__)
+    uint64_t r;
+    asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(count));
+    return r;
+#else
+    return count >= 64 ? 0U : v << count;
+#endif
+}
+
+JLS_HD uint64_t shr64_sat(uint64_t v, uint32_t count)
+{
+#if defined(__CUDA_ARCH__)
+    uint64_t r;
+    asm("shr.u64 %0, %1, %2;" : "=l"(r) : "l"(v), "r"(count));
+    return r;
+#else
+    return count >= 64 ? 0U : v >> count;
+#endif
+}
+
 JLS_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 {
 #if defined(__CUDA_ARCH__)
@@ -109,10 +132,19 @@ JLS_HD uint32_t mulhi32(uint32_t a, uint32_t b)
 #endif
 }
 
-// non-zero iff one of the four bytes of w is 0xFF
+// 0x80 in every byte of w that is 0xFF (exact per byte: the addition never carries out of a byte), 0 elsewhere
 JLS_HD uint32_t has_ff_byte(uint32_t w)
 {
     return ((w & 0x7F7F7F7FU) + 0x01010101U) & w & 0x80808080U;
+}
+
+JLS_HD int32_t popcount32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
 }
 
 JLS_HD int32_t iabs(int32_t v) { return v < 0 ? -v : v; }

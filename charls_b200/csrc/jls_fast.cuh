@@ -391,6 +391,16 @@ constexpr int steady_pixels_per_drain = 64 / (NC * MODE) >= 4 ? 4 : 64 / (NC * M
 #ifndef JLS_STEADY_WRITER
 #define JLS_STEADY_WRITER 1
 #endif
+// 1 (A/B, off): write_steady_21 / write_steady_32 drain one or two words in one step (FastWriter::drain_one_or_two):
+// 94 -> 92 instructions per 32 samples of cfg4, encode 6.78 -> 6.87 ms
+// 1 (A/B, off): the three-component decoder's top-up takes one or two words in one straight-line step
+// (FastReaderT::refill_words) instead of a two-word step for the lanes that need it followed by the one-word loop
+#ifndef JLS_TOP_UP_UNIFIED
+#define JLS_TOP_UP_UNIFIED 0
+#endif
+#ifndef JLS_DRAIN_FUSED
+#define JLS_DRAIN_FUSED 0
+#endif
 // Lossless 16-bit samples need room for ~12-bit code words, everything else (8-bit containers, near-lossless) codes a few
 // bits per sample and drains less often with the short limit.
 template<int NC, bool LOSSLESS, typename S>
@@ -400,11 +410,14 @@ constexpr int writer_mode = !JLS_STEADY_WRITER ? (LOSSLESS && sizeof(S) == 2 ? J
                             : LOSSLESS && sizeof(S) == 2 ? write_steady_32
                                                           : write_steady_16;
 
-// A/B switch (off): L2 eviction hints.  Bit 0: the encoder's slot words are stored `evict_last` (a 32-byte sector of a slot
-// is written by eight separate word stores of one lane; ncu shows 0.45 GB more DRAM writes AND reads than the payload for
-// cfg2: sectors that left L2 half written come back for a read-modify-write).  Bit 1: sample tiles are loaded `evict_first`.
+// L2 eviction hints (profiles/r2g_ab_l2_hints.txt).  Bit 0 (on): the encoder's slot words are stored `evict_last`: encode
+// 6.01 -> 5.84 ms (cfg2), 6.88 -> 6.78 ms (cfg4).  A 32-byte sector of a slot is written by eight separate word stores of one
+// lane, and ncu shows 0.45 GB more DRAM writes AND reads than the payload for cfg2 (sectors written back half full and
+// completed later by a read-modify-write); the hint does not change that traffic, so it is not a capacity effect -- it only
+// shortens the stores.  Bit 1 (off): sample tiles loaded `evict_first` -- DRAM reads 2.6 -> 7.5 GB: a tile row is 32 bytes and
+// the next three tiles of the row live off the 128 bytes L2 fetched for the first.
 #ifndef JLS_L2_HINTS
-#define JLS_L2_HINTS 0
+#define JLS_L2_HINTS 1
 #endif
 
 JLS_HD void store_slot_word(uint32_t* p, uint32_t value)
@@ -415,6 +428,34 @@ JLS_HD void store_slot_word(uint32_t* p, uint32_t value)
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(value), "l"(policy) : "memory");
 #else
     *p = value;
+#endif
+}
+
+// bit 2 of JLS_L2_HINTS (A/B): the decoder's stream words (one 4-byte load per lane and refill, eight loads per sector)
+JLS_HD uint32_t load_stream_word(const uint32_t* p)
+{
+#if defined(__CUDA_ARCH__) && (JLS_L2_HINTS & 4)
+    uint64_t policy;
+    uint32_t value;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(value) : "l"(p), "l"(policy) : "memory");
+    return value;
+#else
+    return *p;
+#endif
+}
+
+// `fallback`, or *p when `wanted`: a predicated load into the register that holds the fallback
+JLS_HD uint32_t load_stream_word_if(bool wanted, const uint32_t* p, uint32_t fallback)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.u32 %0, [%1];\n\t}"
+                 : "+r"(fallback)
+                 : "l"(p), "r"(static_cast<uint32_t>(wanted))
+                 : "memory");
+    return fallback;
+#else
+    return wanted ? *p : fallback;
 #endif
 }
 
@@ -578,8 +619,42 @@ struct FastWriter
     template<int MODE = write_deferred>
     JLS_HD void drain()
     {
+        if (JLS_DRAIN_FUSED && (MODE == write_steady_21 || MODE == write_steady_32))
+        {
+            drain_one_or_two();
+            return;
+        }
         while (nbits >= 32)
             flush_word<MODE == write_wide || is_steady<MODE>>();
+    }
+
+    // The steady modes that see more than one word per drain and lane on average (three samples per pixel, lossless 16-bit
+    // samples): ONE word (nbits < 64) or TWO in the same straight-line step, nbits < 96.  As a loop over flush_word() the
+    // warp makes two trips at nearly every pixel -- 18 lanes active in the first, a few in the second (ncu, cfg4: 21 of the
+    // encoder's 94 instructions per 32 samples).
+    JLS_HD void drain_one_or_two()
+    {
+        if (nbits < 32)
+            return;
+        const bool two = nbits >= 64;
+        const uint32_t a0 = static_cast<uint32_t>(acc), a1 = static_cast<uint32_t>(acc >> 32);
+        const uint32_t t = static_cast<uint32_t>(nbits) & 31U; // nbits - 32 or nbits - 64
+        const uint32_t w1 = funnel_r(two ? a1 : a0, two ? acc_hi : a1, t);
+        const uint32_t w2 = two ? funnel_r(a0, a1, t) : 0U;
+        if (JLS_LIKELY((prev_ff | has_ff_byte(w1) | has_ff_byte(w2)) == 0))
+        {
+            store_slot_word(wp, bswap32(funnel_r(w1, pend, pend_shift)));
+            if (two)
+                store_slot_word(wp + 1, bswap32(funnel_r(w2, w1, pend_shift)));
+            pend = two ? w2 : w1;
+            wp += two ? 2 : 1;
+            nbits -= two ? 64 : 32;
+        }
+        else
+        {
+            while (nbits >= 32)
+                flush_word<true>();
+        }
     }
 
     // steady modes: called after symbols that went through the checked put, restores nbits < 32 for the unchecked ones
@@ -787,27 +862,46 @@ struct FastReaderT
         if (DEPTH == 2)
         {
             ahead = ahead2;
-            ahead2 = guard > 4 ? wptr[2] : 0U; // needed two refills from now
+            ahead2 = guard > 4 ? load_stream_word(wptr + 2) : 0U; // needed two refills from now
         }
         else
         {
-            ahead = guard > 0 ? wptr[1] : 0U; // needed only at the next refill
+            ahead = guard > 0 ? load_stream_word(wptr + 1) : 0U; // needed only at the next refill
         }
         if (JLS_LIKELY(remaining >= 4 && (prev_ff | has_ff_byte(w)) == 0))
         {
             append(w, 32);
         }
+        else if (remaining >= 4)
+        {
+            // Four real bytes with a 0xFF among them or in front: the byte after a 0xFF carries seven bits, its top bit is a
+            // stuffed zero.  Straight-line: the warp walks this path whenever ONE lane meets a 0xFF (three 16-bit samples
+            // per pixel: at a third of all pixels, ncu), and the byte-wise loop below costs 77 instructions.
+            const uint32_t ff = has_ff_byte(w);                   // 0x80 in the bytes that are 0xFF
+            const uint32_t stuffed = (ff >> 8) | (prev_ff << 31); // the top bit of every byte that follows a 0xFF
+            // 0xFF followed by a byte with its top bit set is a marker, and an interval never contains one: the marker
+            // search would have ended it there.  (Only a wrong side table of offsets can lead a reader into one.)
+            if ((w & stuffed) != 0)
+                bad |= 2U;
+            uint32_t bits = w & ~stuffed;
+            // squeeze bit 23, 15 and 7 out where they are stuffed, top one first: what lies above moves down by one,
+            // bits = (hi << (p + 1)) + lo with bit p clear  ->  (hi << p) + lo = bits - ((bits >> 1) & (~0 << p));
+            // a stuffed bit 31 is clear already and only shortens the count
+            bits -= (bits >> 1) & 0xFF800000U & (0U - ((stuffed >> 23) & 1U));
+            bits -= (bits >> 1) & 0xFFFF8000U & (0U - ((stuffed >> 15) & 1U));
+            bits -= (bits >> 1) & 0xFFFFFF80U & (0U - ((stuffed >> 7) & 1U));
+            prev_ff = (ff >> 7) & 1U;
+            append(bits, 32 - popcount32(stuffed));
+        }
         else
         {
-            // bit stuffing (the byte after 0xFF carries 7 bits) and the zero bytes beyond the end of the interval
+            // the last bytes of the interval and the zero bytes beyond its end (bit stuffing as above, byte by byte)
             uint32_t bits = 0;
             int32_t count = 0;
             for (int32_t i = 0; i < 4; ++i)
             {
                 const bool is_virtual = i >= remaining;
                 const uint32_t b = is_virtual ? 0U : (w >> (24 - 8 * i)) & 0xFFU;
-                // 0xFF followed by a byte with its top bit set is a marker, and an interval never contains one: the marker
-                // search would have ended it there.  (Only a wrong side table of offsets can lead a reader into one.)
                 if (prev_ff && (b & 0x80U) != 0)
                     bad |= 2U;
                 const int32_t take = prev_ff ? 7 : 8;
@@ -844,12 +938,12 @@ struct FastReaderT
 #if defined(__CUDA_ARCH__)
             __builtin_assume(__isGlobal(wptr));
 #endif
-            ahead = guard > 0 ? wptr[1] : 0U;
-            ahead2 = guard > 4 ? wptr[2] : 0U;
+            ahead = guard > 0 ? load_stream_word(wptr + 1) : 0U;
+            ahead2 = guard > 4 ? load_stream_word(wptr + 2) : 0U;
             // 64 bits at bit `valid` of the window; everything below the valid bits is zero
             const uint64_t v = (static_cast<uint64_t>(w1) << 32) | w2;
-            const uint64_t upper = valid < 64 ? v >> valid : 0U;
-            const uint64_t lower = valid > 0 ? v << (64 - valid) : 0U;
+            const uint64_t upper = shr64_sat(v, static_cast<uint32_t>(valid));
+            const uint64_t lower = shl64_sat(v, static_cast<uint32_t>(64 - valid));
             c3 |= static_cast<uint32_t>(upper >> 32);
             c2 |= static_cast<uint32_t>(upper);
             c1 |= static_cast<uint32_t>(lower >> 32);
@@ -864,14 +958,70 @@ struct FastReaderT
         }
     }
 
+    // DEPTH == 2 (three 16-bit samples per pixel take more than one word per pixel and lane), valid <= full_mark: ONE word
+    // (64 < valid) or TWO (valid <= 64) in the same straight-line step.  Round 1 had a two-word step for the lanes with
+    // valid <= 64 followed by the one-word loop for everybody: 5 lanes walked the warp through the first (57 instructions),
+    // 26 through the second (35), at every pixel (profiles/r2_notes.md).  All words come from registers that were loaded at
+    // an earlier top-up, and the loads issued here go straight into `ahead` and `ahead2`: no instruction reads a register
+    // whose load is still in flight.
+    JLS_HD void refill_words()
+    {
+        const bool two = valid <= 64;
+        const uint32_t w1 = bswap32(funnel_r(cur, ahead, shift));
+        const uint32_t w2 = two ? bswap32(funnel_r(ahead, ahead2, shift)) : 0U;
+        if (JLS_LIKELY(remaining >= 8 && (prev_ff | has_ff_byte(w1) | has_ff_byte(w2)) == 0))
+        {
+            const int32_t bytes = two ? 8 : 4;
+            cur = two ? ahead2 : ahead;
+            wptr += two ? 2 : 1;
+            guard -= bytes;
+            remaining -= bytes;
+#if defined(__CUDA_ARCH__)
+            __builtin_assume(__isGlobal(wptr));
+#endif
+            // A one-word lane keeps the word it holds as `ahead2` and loads one new word, a two-word lane loads two.  The load
+            // is predicated and writes the register in place: as a select between the register and a loaded value it gets a
+            // move behind the load, and the move waits for the load (decode 8.6 -> 9.4 ms); loading both words in every lane
+            // avoids the move but adds 70 % to the L1 wavefronts of the stream loads (32 lanes, 32 lines: 9.7 ms).
+            ahead = load_stream_word_if(two && guard > 0, wptr + 1, two ? 0U : ahead2);
+            ahead2 = load_stream_word_if(guard > 4, wptr + 2, 0U);
+            // 32 or 64 bits at bit `valid` of the window; everything below the valid bits is zero
+            const uint64_t v = (static_cast<uint64_t>(w1) << 32) | w2;
+            const uint64_t upper = shr64_sat(v, static_cast<uint32_t>(valid));
+            const uint64_t lower = two ? shl64_sat(v, static_cast<uint32_t>(64 - valid)) : v >> (valid - 64);
+            c3 |= static_cast<uint32_t>(upper >> 32);
+            c2 |= static_cast<uint32_t>(upper);
+            c1 |= static_cast<uint32_t>(lower >> 32);
+            c0 |= static_cast<uint32_t>(lower);
+            valid += 8 * bytes;
+        }
+        else
+        {
+            refill();
+        }
+    }
+
+    // what top_up() guarantees: DEPTH == 2 stops at three symbols' worth (one pixel), where a lane that arrives nearly empty
+    // would need a third word
+    static constexpr int32_t topped_up_bits = JLS_TOP_UP_UNIFIED && DEPTH == 2 ? 3 * STEADY_BITS : full_mark + 1;
+
     // the pixel loop's cadence call (all lanes of a warp together)
     JLS_HD void top_up()
     {
         if (valid <= full_mark)
         {
-            if (DEPTH == 2 && valid <= 64)
-                refill_pair();
-            refill();
+            if (JLS_TOP_UP_UNIFIED && DEPTH == 2)
+            {
+                refill_words();
+                if (JLS_UNLIKELY(valid < topped_up_bits))
+                    refill();
+            }
+            else
+            {
+                if (DEPTH == 2 && valid <= 64)
+                    refill_pair();
+                refill();
+            }
         }
     }
 
@@ -911,8 +1061,8 @@ struct FastReaderT
     // only takes code words of up to `steady_bits` bits (full_mark + 1 - 4 * 24 >= 24), and every other way of
     // consuming bits (long code words, run mode) ends with a top_up() of its own.
     static constexpr int32_t steady_bits = STEADY_BITS;
-    static constexpr int32_t steady_symbols = (full_mark + 1) / STEADY_BITS; // 4 (97 - 4 * 24 >= 0 ...) or 8
-    static_assert(full_mark + 1 - (steady_symbols - 1) * steady_bits >= steady_bits, "the last symbol of a group finds its bits");
+    static constexpr int32_t steady_symbols = topped_up_bits / STEADY_BITS; // 4 (97 - 4 * 24 >= 0 ...), 8, or 3 (DEPTH == 2)
+    static_assert(topped_up_bits - (steady_symbols - 1) * steady_bits >= steady_bits, "the last symbol of a group finds its bits");
 
     JLS_HD int32_t get_golomb_steady(const HotParams& h, int32_t k, int32_t escape)
     {

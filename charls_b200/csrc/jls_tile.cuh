@@ -162,6 +162,10 @@ __device__ __forceinline__ void tile_store(const uint32_t* tile, uint8_t* pixels
         const TileWalk<TW> walk(lane, static_cast<uint32_t>(stride));
         uint8_t* destination = pixels + static_cast<size_t>(first_line) * stride + tile_index * (TW * 4);
         unsigned source = static_cast<unsigned>(__cvta_generic_to_shared(tile));
+#if defined(JLS_L2_HINTS) && (JLS_L2_HINTS & 8)
+        uint64_t store_policy; // A/B: decoded tiles are written once and not read again by this kernel
+        asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(store_policy));
+#endif
 #pragma unroll
         for (int g = 0; g < TileWalk<TW>::groups; ++g)
         {
@@ -170,7 +174,13 @@ __device__ __forceinline__ void tile_store(const uint32_t* tile, uint8_t* pixels
             {
                 uint32_t word;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(source + walk.shared_offset[j]) : "memory");
+#if defined(JLS_L2_HINTS) && (JLS_L2_HINTS & 8)
+                asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(destination + walk.global_offset[j]), "r"(word),
+                             "l"(store_policy)
+                             : "memory");
+#else
                 *reinterpret_cast<uint32_t*>(destination + walk.global_offset[j]) = word;
+#endif
             }
             destination += TileWalk<TW>::rows * stride;
             source += TileWalk<TW>::rows * (TW + 1) * 4U;
