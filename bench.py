@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step (128 x 8 GPUs = BASELINE configs[4])")
     ap.add_argument("--e2e-frames", type=int, default=32)
     ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-one-part-threads", type=int, default=16, help="host threads of the headline e2e run (one image per thread)")
     ap.add_argument("--e2e-inflight", type=int, default=4,
                     help="codec objects every e2e host thread keeps in flight through the two-part calls (charlsx_*_begin / _end); "
                          "1 = the one-part reference calls only")
@@ -576,7 +577,7 @@ def run_gpu_arm(args):
         # Headline: the reference's own calls (charls_jpegls_encoder_encode_from_buffer / charls_jpegls_decoder_decode_to_buffer,
         # synchronous), one image in flight per host thread.  The ranks of a box share its cores: callers mostly wait for the
         # GPU, so twice the cores are handed out, but not more (waiters that find no core slow everybody down).
-        threads_one = max(1, min(16, effective_cpus(), max(4, 2 * effective_cpus() // world)))
+        threads_one = max(1, min(args.e2e_one_part_threads, effective_cpus(), max(4, 2 * effective_cpus() // world)))
         value_one_part, e2e_sizes = measure(threads_one, 1)
         # Beside it: the two-part forms of the same calls (charlsx_*_begin / _end: "issue" and "complete"), several codec objects
         # in flight per host thread -- the same throughput from half as many threads
