@@ -383,10 +383,23 @@ int32_t Engine::ensure(Buffer& buffer, size_t bytes, bool pinned)
     ++buffer_generation_; // captured graphs hold the old address
     const size_t capacity = align_up(bytes + bytes / 8 + 256, 256);
     void* data = nullptr;
+    // Fresh memory is zeroed once (buffers only grow, so this is rare): kernels read whole aligned words around the ends of
+    // streams and the outcome copy carries a pad word, all masked or ignored -- but initcheck (tools/sanitize_gpu.sh) then has
+    // nothing to report, and nothing a caller gets back can depend on what the allocator handed out.
     if (pinned)
+    {
         JLS_CUDA(cudaMallocHost(&data, capacity));
+        std::memset(data, 0, capacity);
+    }
     else
+    {
         JLS_CUDA(cudaMalloc(&data, capacity));
+        buffer.data = data; // owned from here on: an early return below leaves it to release()
+        buffer.capacity = capacity;
+        buffer.pinned = false;
+        JLS_CUDA(cudaMemset(data, 0, capacity));
+        JLS_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); // kernels run on non-blocking streams: the memset must be over
+    }
     buffer.data = data;
     buffer.capacity = capacity;
     buffer.pinned = pinned;

@@ -370,7 +370,9 @@ CHARLS_B200_API charls_jpegls_errc charlsx_jpegls_encoder_set_offset_table(charl
 typedef struct charlsx_batch_image
 {
     void* pixels;           /* device: samples of the frame (encode: input, decode: output), 16-byte aligned */
-    void* stream;           /* device: complete JPEG-LS stream (encode: output, decode: input) */
+    void* stream;           /* device: complete JPEG-LS stream (encode: output, decode: input).  The decoder loads the stream in
+                             * aligned 32-bit words: up to three bytes on either side of it, inside the words that hold its first
+                             * and last byte, are read and ignored. */
     size_t stream_capacity; /* encode: capacity of `stream`; decode: size of the stream in bytes */
     size_t stream_size;     /* encode: bytes written (out) */
     int32_t status;         /* charls_jpegls_errc of this frame (out) */
