@@ -34,6 +34,9 @@ WORKLOADS = {
     "cfg2": (4096, 4096, 8, 1, 0, 0, 0),   # BASELINE.json configs[1]: 4096x4096 8-bit grayscale lossless
     "cfg3": (4096, 4096, 12, 1, 2, 0, 0),  # configs[2]: 12-bit NEAR=2
     "cfg4": (2048, 2048, 16, 3, 0, 2, 1),  # configs[3]: 16-bit RGB, ILV sample, HP1
+    # not in BASELINE.json: the two shapes that take the kernels without shared-memory tiles (k_encode_fast / k_decode_fast)
+    "rgb8line": (2048, 2048, 8, 3, 0, 1, 0),  # line interleave: a lane gathers its component from RGBRGB... rows
+    "odd8": (4095, 4096, 8, 1, 0, 0, 0),      # rows of 4095 bytes: not 4-byte aligned
 }
 METRIC = "MPixels/s encode+decode"
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcharls_ref.so")
@@ -758,8 +761,9 @@ def run_gpu_arm(args):
                 "algorithmic_bytes_per_launch": algorithmic}
 
     fast = args.restart_interval == 1
-    roofs = {"encode": roof("k_encode_tiled" if fast else "k_encode_general", t_enc),
-             "decode": roof("k_decode_tiled" if fast else "k_decode_general", t_dec)}
+    tiled = ilv != 1 and (w * cc * (1 if bits <= 8 else 2)) % 4 == 0  # else the per-lane kernels without shared-memory tiles
+    family = ("tiled" if tiled else "fast") if fast else "general"
+    roofs = {"encode": roof(f"k_encode_{family}", t_enc), "decode": roof(f"k_decode_{family}", t_dec)}
     dominant = dict(roofs["encode"] if t_enc >= t_dec else roofs["decode"])
     other_kernel = roofs["decode"] if t_enc >= t_dec else roofs["encode"]
     dominant["other_kernel"] = other_kernel["kernel"]

@@ -918,7 +918,10 @@ int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, s
     JLS_CHECK(prepare_staging());
     const size_t row_bytes = row_bytes_of(p);
     const size_t frame_bytes = stride * (static_cast<size_t>(p.height) - 1) + row_bytes;
-    const size_t frame_pitch = align_up(stride * static_cast<size_t>(p.height), 256); // distance between staged frames
+    // Rows whose distance is not a multiple of four bytes would take the kernels without shared-memory tiles (half the speed):
+    // the staged copy gets an aligned pitch instead, the copy engine does the re-pitching on the way in.
+    const size_t staged_stride = stride % 4 == 0 ? stride : align_up(row_bytes, 16);
+    const size_t frame_pitch = align_up(staged_stride * static_cast<size_t>(p.height), 256); // distance between staged frames
     const size_t slot_bytes = worst_case_interval_bytes(p, p.lines_per_interval);
     size_t stream_slot = header_size + static_cast<size_t>(p.interval_count) * (slot_bytes + 2) + 2; // nothing is longer
     size_t largest_capacity = 0;
@@ -945,8 +948,14 @@ int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, s
         JLS_CUDA(cudaStreamWaitEvent(copy_in_, out_done_[s], 0));
         const size_t first = j * chunk, n = frames_in(j);
         for (size_t k = 0; k < n; ++k)
-            JLS_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch, frames[first + k].pixels, frame_bytes,
-                                     cudaMemcpyHostToDevice, copy_in_));
+        {
+            uint8_t* staged_frame = static_cast<uint8_t*>(stage_pixels_[s].data) + k * frame_pitch;
+            if (staged_stride == stride)
+                JLS_CUDA(cudaMemcpyAsync(staged_frame, frames[first + k].pixels, frame_bytes, cudaMemcpyHostToDevice, copy_in_));
+            else
+                JLS_CUDA(cudaMemcpy2DAsync(staged_frame, staged_stride, frames[first + k].pixels, stride, row_bytes,
+                                           static_cast<size_t>(p.height), cudaMemcpyHostToDevice, copy_in_));
+        }
         JLS_CUDA(cudaEventRecord(in_done_[s], copy_in_));
         return 0;
     };
@@ -961,7 +970,7 @@ int32_t Engine::encode_batch_host(const CodecParams& p, const uint8_t* header, s
         }
         Engine& engine = engine_of(j);
         JLS_CUDA(cudaStreamWaitEvent(engine.stream_, in_done_[s], 0));
-        return engine.encode_batch_begin(p, header, header_size, staged[s].data(), n, stride, engine.stream_, table);
+        return engine.encode_batch_begin(p, header, header_size, staged[s].data(), n, staged_stride, engine.stream_, table);
     };
     int32_t first_error = 0;
     uint32_t launches = 0;
@@ -1015,7 +1024,8 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
     bool with_tables[staging_slots] = {};
     const size_t row_bytes = row_bytes_of(p);
     const size_t frame_bytes = stride * (static_cast<size_t>(p.height) - 1) + row_bytes;
-    const size_t frame_pitch = align_up(stride * static_cast<size_t>(p.height), 256);
+    const size_t staged_stride = stride % 4 == 0 ? stride : align_up(row_bytes, 16); // see encode_batch_host
+    const size_t frame_pitch = align_up(staged_stride * static_cast<size_t>(p.height), 256);
     size_t stream_slot = 0;
     for (size_t i = 0; i < count; ++i)
         stream_slot = frames[i].stream_capacity > stream_slot ? frames[i].stream_capacity : stream_slot;
@@ -1054,7 +1064,7 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
         Engine& engine = engine_of(j);
         JLS_CUDA(cudaStreamWaitEvent(engine.stream_, in_done_[s], 0));
         with_tables[s] = all_frames_have_tables(p, staged[s].data(), n);
-        return engine.decode_batch_begin(p, staged[s].data(), n, stride, engine.stream_, with_tables[s]);
+        return engine.decode_batch_begin(p, staged[s].data(), n, staged_stride, engine.stream_, with_tables[s]);
     };
     int32_t first_error = 0;
     uint32_t launches = 0;
@@ -1067,7 +1077,7 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
         if (status != 0 && with_tables[s])
         {
             // not a clean decode with the side tables: once more by marker search (decode_scan_to_host_end)
-            JLS_CHECK(engine.decode_batch_begin(p, staged[s].data(), n, stride, engine.stream_, false));
+            JLS_CHECK(engine.decode_batch_begin(p, staged[s].data(), n, staged_stride, engine.stream_, false));
             status = engine.decode_batch_end(staged[s].data(), n, engine.stream_);
         }
         launches += engine.last_launches_;
@@ -1078,8 +1088,13 @@ int32_t Engine::decode_batch_host(const CodecParams& p, BatchFrame* frames, size
         {
             frames[first + k].status = staged[s][k].status;
             frames[first + k].stream_size = staged[s][k].stream_size;
-            if (staged[s][k].status == 0)
+            if (staged[s][k].status != 0)
+                continue;
+            if (staged_stride == stride)
                 JLS_CUDA(cudaMemcpyAsync(frames[first + k].pixels, staged[s][k].pixels, frame_bytes, cudaMemcpyDeviceToHost, copy_out_));
+            else
+                JLS_CUDA(cudaMemcpy2DAsync(frames[first + k].pixels, stride, staged[s][k].pixels, staged_stride, row_bytes,
+                                           static_cast<size_t>(p.height), cudaMemcpyDeviceToHost, copy_out_));
         }
         JLS_CUDA(cudaEventRecord(out_done_[s], copy_out_));
         return 0;

@@ -581,7 +581,8 @@ def test_host_batch_interface(product, oracle):
     from charls_b200.batch import BatchCodec
 
     for (w, h, bits, cc, near, ilv, xf, n) in ((96, 40, 8, 1, 0, 0, 0, 7), (50, 21, 12, 1, 2, 0, 0, 3), (33, 17, 16, 3, 0, 2, 1, 5),
-                                               (512, 300, 8, 1, 0, 0, 0, 70)):
+                                               (512, 300, 8, 1, 0, 0, 0, 70), (131, 45, 8, 1, 0, 0, 0, 9), (67, 30, 8, 3, 0, 2, 0, 6)):
+        # (rows of 198, 131 and 201 bytes are not 4-byte aligned: the staged copies get an aligned pitch, engine.cu)
         frames = [s_mixed(h, w, bits, cc, seed=50 + i, layout="interleaved") for i in range(n)]
         bc = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, lib=product)
         streams = [np.zeros(bc.stream_capacity * 2, np.uint8) for _ in range(n)]
