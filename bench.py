@@ -36,7 +36,7 @@ WORKLOADS = {
     "cfg4": (2048, 2048, 16, 3, 0, 2, 1),  # configs[3]: 16-bit RGB, ILV sample, HP1
     # not in BASELINE.json: the two shapes that take the kernels without shared-memory tiles (k_encode_fast / k_decode_fast)
     "rgb8line": (2048, 2048, 8, 3, 0, 1, 0),  # line interleave: a lane gathers its component from RGBRGB... rows
-    "odd8": (4095, 4096, 8, 1, 0, 0, 0),      # rows of 4095 bytes: not 4-byte aligned
+    "odd8": (4095, 4096, 8, 1, 0, 0, 0),      # rows of 4095 bytes: tightly packed they are not 4-byte aligned (--row-pitch 4096: tiles)
 }
 METRIC = "MPixels/s encode+decode"
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcharls_ref.so")
@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--no-offset-table", action="store_true",
                     help="batch streams without the side table of interval offsets (APP11 \"JLS-OFFT\", include/charls_b200.h): the "
                          "decoder then searches every stream for its restart markers (three more kernels)")
+    ap.add_argument("--row-pitch", type=int, default=0,
+                    help="bytes between the lines of the device frames (0 = tightly packed); e.g. --workload odd8 --row-pitch 4096")
     ap.add_argument("--content", default="smooth", choices=["smooth", "noise", "flat"],
                     help="smooth = S_smooth (the metric's input); noise (uniform, incompressible) and flat (all zero, pure run "
                          "mode) bracket it (SURVEY.md 8d)")
@@ -473,12 +475,22 @@ def run_gpu_arm(args):
     w, h, bits, cc, near, ilv, xf = WORKLOADS[args.workload]
     F = args.frames
     frames = make_frames(torch, device, F, args.workload, first_seed=1234 + rank * F, content=args.content)
+    if args.row_pitch:
+        # the same frames with `row_pitch` bytes between their lines: views into wider tensors
+        assert cc == 1 and args.row_pitch % frames.element_size() == 0 and args.row_pitch >= w * frames.element_size()
+        wide = torch.zeros((F, h, args.row_pitch // frames.element_size()), device=device, dtype=frames.dtype)
+        wide[:, :, :w] = frames
+        frames = wide[:, :, :w]
     codec = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf,
-                       restart_interval=args.restart_interval, offset_table=not args.no_offset_table, lib=lib)
+                       restart_interval=args.restart_interval, offset_table=not args.no_offset_table, row_stride=args.row_pitch,
+                       lib=lib)
     if args.content == "noise":
         codec.stream_capacity *= 2  # incompressible input expands (about 9.5 bits per 8-bit sample)
     streams = torch.empty((F, codec.stream_capacity), device=device, dtype=torch.uint8)
-    decoded = torch.empty_like(frames)
+    if args.row_pitch:
+        decoded = torch.zeros((F, h, args.row_pitch // frames.element_size()), device=device, dtype=frames.dtype)[:, :, :w]
+    else:
+        decoded = torch.empty_like(frames)
     raw_bytes = frames[0].numel() * frames.element_size()
 
     def step():
@@ -761,7 +773,8 @@ def run_gpu_arm(args):
                 "algorithmic_bytes_per_launch": algorithmic}
 
     fast = args.restart_interval == 1
-    tiled = ilv != 1 and (w * cc * (1 if bits <= 8 else 2)) % 4 == 0  # else the per-lane kernels without shared-memory tiles
+    # the per-lane kernels without shared-memory tiles: line interleave, and a distance between rows that is not a multiple of 4
+    tiled = ilv != 1 and (args.row_pitch or w * cc * (1 if bits <= 8 else 2)) % 4 == 0
     family = ("tiled" if tiled else "fast") if fast else "general"
     roofs = {"encode": roof(f"k_encode_{family}", t_enc), "decode": roof(f"k_decode_{family}", t_dec)}
     dominant = dict(roofs["encode"] if t_enc >= t_dec else roofs["decode"])

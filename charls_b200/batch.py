@@ -14,13 +14,14 @@ class BatchCodec:
     """Encodes / decodes batches of equally shaped frames that live in CUDA tensors."""
 
     def __init__(self, width, height, bits_per_sample, component_count=1, *, near_lossless=0, interleave_mode=0,
-                 color_transformation=0, restart_interval=1, offset_table=False, lib: CharlsLibrary | None = None):
+                 color_transformation=0, restart_interval=1, offset_table=False, row_stride=0, lib: CharlsLibrary | None = None):
         """offset_table: write (encode) / look for (decode) the side table of interval offsets in the streams' headers
-        (CHARLSX_BATCH_OFFSET_TABLE, include/charls_b200.h)."""
+        (CHARLSX_BATCH_OFFSET_TABLE, include/charls_b200.h).  row_stride: bytes between the lines of a frame (0 = tightly packed);
+        device frames whose stride is a multiple of 4 take the tile kernels whatever their width."""
         self.lib = lib or default_library()
         self.params = BatchParams(
             FrameInfo(width, height, bits_per_sample, component_count), near_lossless, interleave_mode, color_transformation,
-            restart_interval, 0, 1 if offset_table and restart_interval else 0,
+            restart_interval, row_stride, 1 if offset_table and restart_interval else 0,
         )
         self._h = self.lib.charlsx_batch_create()
         if not self._h:

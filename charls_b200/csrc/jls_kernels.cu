@@ -1104,9 +1104,9 @@ size_t tiled_dynamic_shared_bytes(const CodecParams& p)
 // ---------------------------------------------------------------------------------------------------------------------
 bool rows_tileable(const CodecParams& p, bool rows_word_aligned)
 {
-    const size_t samples_per_pixel = p.interleave == ilv_sample ? static_cast<size_t>(p.components) : 1U;
-    return rows_word_aligned && p.interleave != ilv_line && p.t3 < context_lut_capacity && p.reset < reciprocal_lut_capacity &&
-           (static_cast<size_t>(p.width) * samples_per_pixel * static_cast<size_t>(p.sample_bytes)) % 4U == 0;
+    // rows need not END on a word boundary: the last tile of a row is copied word by word with the row's length in hand
+    // (tile_load_async, tile_store), and a stride that is a multiple of four leaves room behind such a row
+    return rows_word_aligned && p.interleave != ilv_line && p.t3 < context_lut_capacity && p.reset < reciprocal_lut_capacity;
 }
 
 template<int NC, bool LL, typename S>

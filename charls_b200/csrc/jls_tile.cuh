@@ -111,7 +111,8 @@ __device__ __forceinline__ void tile_load_async(uint32_t* tile, const uint8_t* p
         const bool inside = byte < row_bytes;
         const uint32_t line = min(first_line + r, last_line);
         const uint8_t* source = pixels + static_cast<size_t>(line) * stride + (inside ? byte : 0);
-        cp_async_4(tile + r * SW + w, source, inside ? 4 : 0);
+        // a row that does not end on a word boundary: only its own bytes are read, the rest of the word is zero-filled
+        cp_async_4(tile + r * SW + w, source, inside ? min(4, row_bytes - byte) : 0);
     }
     cp_async_commit();
 }
@@ -152,6 +153,13 @@ __device__ __forceinline__ void tile_load_bulk(uint32_t tile_shared, uint32_t ro
 }
 
 // Writes tile `tile_index` back: row r goes to line first_line + r if bit r of `row_mask` is set.
+// one to three bytes, once per row at most: kept out of line so that the tile kernels' register allocation does not see it
+__device__ __noinline__ void store_row_tail(uint8_t* destination, uint32_t word, int32_t count)
+{
+    for (int32_t b = 0; b < count; ++b)
+        destination[b] = static_cast<uint8_t>(word >> (8 * b));
+}
+
 template<int TW>
 __device__ __forceinline__ void tile_store(const uint32_t* tile, uint8_t* pixels, size_t stride, uint32_t first_line,
                                            uint32_t row_mask, int32_t row_bytes, int32_t tile_index, uint32_t lane)
@@ -194,9 +202,16 @@ __device__ __forceinline__ void tile_store(const uint32_t* tile, uint8_t* pixels
         const uint32_t r = index / TW;
         const uint32_t w = index - r * TW;
         const int32_t byte = tile_index * (TW * 4) + static_cast<int32_t>(w) * 4;
-        if (byte < row_bytes && ((row_mask >> r) & 1U) != 0)
+        if (byte + 4 <= row_bytes && ((row_mask >> r) & 1U) != 0)
             *reinterpret_cast<uint32_t*>(pixels + static_cast<size_t>(first_line + r) * stride + byte) = tile[r * (TW + 1) + w];
     }
+    // The last one to three bytes of rows that do not end on a word boundary, lane r for row r: what follows them belongs to
+    // the caller (or to the next row when the stride leaves no room).
+    const int32_t tail_byte = row_bytes & ~3;
+    if ((row_bytes & 3) != 0 && tail_byte >= tile_index * (TW * 4) && tail_byte < (tile_index + 1) * (TW * 4) &&
+        ((row_mask >> lane) & 1U) != 0)
+        store_row_tail(pixels + static_cast<size_t>(first_line + lane) * stride + tail_byte,
+                       tile[lane * (TW + 1) + (tail_byte - tile_index * (TW * 4)) / 4], row_bytes & 3);
 }
 
 } // namespace jls

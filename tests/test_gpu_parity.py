@@ -82,6 +82,27 @@ def test_scalar_sweep_vs_oracle(product, oracle, bits):
                     assert np.array_equal(px, expected), (gen.__name__, h, w, bits, near, ri)
 
 
+def test_every_way_a_row_can_end_inside_a_tile(product, oracle):
+    """The tile kernels' last tile of a row: every number of pixels it can hold, rows that end on and inside a word
+    (8-bit: widths 29..68 across the 32- and 64-byte tiles of encoder and decoder; 16-bit, RGB likewise), more lines than a
+    warp has lanes.  Bytes against the oracle, samples against the oracle's decode."""
+    cases = [(8, 1, 0, 0, w) for w in list(range(29, 69)) + [95, 96, 97, 127, 129]]
+    cases += [(16, 1, 0, 0, w) for w in range(13, 36)]
+    cases += [(12, 1, 0, 0, w) for w in (31, 33, 34)]
+    cases += [(8, 3, 2, 0, w) for w in range(9, 36)]
+    cases += [(16, 3, 2, 1, w) for w in range(5, 20)]
+    cases += [(8, 4, 2, 0, w) for w in (7, 9, 15, 17)] + [(16, 2, 2, 0, w) for w in (7, 9, 15, 17)]
+    for bits, cc, ilv, xf, w in cases:
+        img = s_mixed(37, w, bits, cc, seed=w, layout="interleaved")
+        for near in ((0, 2) if xf == 0 else (0,)):
+            got = encode(product, img, bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf)
+            want = oracle.encode_image(img, bits, near=near, ilv=ilv, xform=xf, ri=1)
+            assert payloads(got) == payloads(want), (bits, cc, w, near)
+            expected, _ = oracle.decode_image(got)
+            px, _, _ = codec.decode(got, lib=product)
+            assert np.array_equal(px, expected), (bits, cc, w, near)
+
+
 @pytest.mark.parametrize("bits", [8, 16])
 def test_color_sweep_vs_oracle(product, oracle, bits):
     for cc in (2, 3, 4):
@@ -771,3 +792,45 @@ def test_one_frame_coded_in_strips(product, oracle):
             assert sharding.stitch_strips(strips, [len(r) for r in ranges]) == whole, (h, w, bits, world)
             lines = [codec.decode(part, lib=product)[0] for part in sharding.split_stream(whole, world) if part is not None]
             assert np.array_equal(np.concatenate(lines, axis=0), expected), (h, w, bits, world)
+
+
+def test_batch_rows_that_do_not_end_on_a_word_boundary(product, oracle):
+    """Device frames with a row stride that is a multiple of four but rows of 131 / 67 / 198 bytes: they take the tile
+    kernels (the last tile of a row is copied with the row's length in hand), the streams are those of the single-image ABI,
+    and a decode leaves the bytes between the end of a row and the next row alone."""
+    import torch
+
+    from charls_b200.batch import BatchCodec
+
+    device = torch.device("cuda", 0)
+    for (w, h, bits, cc, near, ilv, xf, pitch) in ((131, 45, 8, 1, 0, 0, 0, 132), (131, 45, 8, 1, 2, 0, 0, 144), (67, 70, 8, 1, 0, 0, 0, 68),
+                                                   (33, 40, 16, 3, 0, 2, 1, 200), (77, 35, 8, 3, 0, 2, 0, 232), (99, 33, 12, 1, 0, 0, 0, 200)):
+        n = 4
+        sample_bytes = 1 if bits <= 8 else 2
+        row_bytes = w * cc * sample_bytes
+        assert pitch % 4 == 0 and pitch >= row_bytes and row_bytes % 4 != 0
+        frames_np = [s_mixed(h, w, bits, cc, seed=300 + i, layout="interleaved") for i in range(n)]
+        padded = np.full((n, h, pitch), 0xAB, np.uint8)
+        for i, f in enumerate(frames_np):
+            padded[i, :, :row_bytes] = np.ascontiguousarray(f).view(np.uint8).reshape(h, row_bytes)
+        t = torch.from_numpy(padded).to(device)
+        bc = BatchCodec(w, h, bits, cc, near_lossless=near, interleave_mode=ilv, color_transformation=xf, row_stride=pitch, lib=product)
+        streams = torch.zeros((n, bc.stream_capacity * 2), dtype=torch.uint8, device=device)
+        sizes = bc.encode(t, streams)
+        host = streams.cpu().numpy()
+        for i in range(n):
+            single = encode(product, frames_np[i], bits, near_lossless=near, interleave_mode=ilv, color_transformation=xf)
+            assert host[i, : sizes[i]].tobytes() == single, (w, h, bits, i)
+        out = torch.full_like(t, 0xCD)
+        bc.decode(streams, sizes, out)
+        got = out.cpu().numpy()
+        assert (got[:, :, row_bytes:] == 0xCD).all(), (w, h, bits, "bytes behind the rows were written")
+        for i in range(n):
+            expected, _ = oracle.decode_image(host[i, : sizes[i]].tobytes())
+            rows = np.ascontiguousarray(got[i, :, :row_bytes])
+            rows = rows.view(np.uint16) if bits > 8 else rows
+            assert np.array_equal(rows.reshape(expected.shape), expected), (w, h, bits, i)
+        bc.close()
+
+
+
