@@ -14,6 +14,9 @@
 #include <cstring>
 #include <cuda_runtime.h>
 #include <mutex>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <vector>
 
 namespace jls {
@@ -174,7 +177,44 @@ Trace g_trace;
 const int g_connections_set = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 
 std::atomic<int> g_borrowed{0};           // engines that codec objects hold right now
-constexpr int blocking_sync_threshold = 6; // see Engine::wait_for
+// Codec objects in flight from which on a waiting caller sleeps instead of spinning (Engine::wait_for): at least 6, and not
+// before there are more objects in flight than this process has cores to spin on -- the cores it may run on (affinity, capped by
+// a cgroup CPU quota) divided by the GPUs of the box, since a multi-GPU job runs one such process per GPU.  Measured with 16
+// callers on a 16-core single-GPU box: 26.8 GPix/s when they spin, 25.4 when they sleep (profiles/r2k_copy_pattern_probe.txt);
+// with 8 processes x 8 callers on the 32 vCPUs of an 8-GPU box they have to sleep.
+int blocking_sync_threshold()
+{
+    static const int value = [] {
+        unsigned cpus = std::thread::hardware_concurrency();
+#if defined(__linux__)
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0)
+            cpus = static_cast<unsigned>(CPU_COUNT(&set));
+        if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r"))
+        {
+            char quota[32] = {};
+            unsigned long period = 0;
+            if (std::fscanf(f, "%31s %lu", quota, &period) == 2 && period > 0 && std::strcmp(quota, "max") != 0)
+            {
+                const unsigned long allowed = (std::strtoul(quota, nullptr, 10) + period - 1) / period;
+                if (allowed > 0 && allowed < cpus)
+                    cpus = static_cast<unsigned>(allowed);
+            }
+            std::fclose(f);
+        }
+#endif
+        int devices = 1;
+        if (cudaGetDeviceCount(&devices) != cudaSuccess || devices < 1)
+        {
+            cudaGetLastError();
+            devices = 1;
+        }
+        const int per_device = static_cast<int>(cpus) / devices;
+        return per_device + 1 > 6 ? per_device + 1 : 6;
+    }();
+    return value;
+}
 } // namespace
 
 // The device a new piece of work belongs to: the one set with charlsx_set_device, else the calling thread's current device
@@ -249,14 +289,14 @@ void Engine::drop_pooled_except(int device) noexcept
 // Waits until `stream` has drained.  A lone caller spins (lowest latency).  When many codec objects are in flight -- one
 // host thread per image is how the reference API gets used in parallel -- spinning threads eat the cores (and any CPU
 // quota of the container) the other callers need to feed the GPU, so from `blocking_sync_threshold` borrowed engines on
-// the thread sleeps on an event instead.  CHARLS_B200_BLOCKING_SYNC=0 / 1 forces one behaviour.
+// the thread sleeps on an event instead (blocking_sync_threshold() above).  CHARLS_B200_BLOCKING_SYNC=0 / 1 forces one behaviour.
 int32_t Engine::wait_for(CUstream_st* stream)
 {
     static const int forced = [] {
         const char* value = std::getenv("CHARLS_B200_BLOCKING_SYNC");
         return value && (value[0] == '0' || value[0] == '1') ? value[0] - '0' : -1;
     }();
-    const bool blocking = forced >= 0 ? forced == 1 : g_borrowed.load(std::memory_order_relaxed) >= blocking_sync_threshold;
+    const bool blocking = forced >= 0 ? forced == 1 : g_borrowed.load(std::memory_order_relaxed) >= blocking_sync_threshold();
     if (!blocking)
     {
         JLS_CUDA(cudaStreamSynchronize(stream));
