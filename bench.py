@@ -34,9 +34,10 @@ WORKLOADS = {
     "cfg2": (4096, 4096, 8, 1, 0, 0, 0),   # BASELINE.json configs[1]: 4096x4096 8-bit grayscale lossless
     "cfg3": (4096, 4096, 12, 1, 2, 0, 0),  # configs[2]: 12-bit NEAR=2
     "cfg4": (2048, 2048, 16, 3, 0, 2, 1),  # configs[3]: 16-bit RGB, ILV sample, HP1
-    # not in BASELINE.json: the two shapes that take the kernels without shared-memory tiles (k_encode_fast / k_decode_fast)
+    # not in BASELINE.json: line interleave (kernels without shared-memory tiles, k_encode_fast / k_decode_fast) and rows that
+    # do not start on word boundaries (copied to an aligned pitch around the tile kernels)
     "rgb8line": (2048, 2048, 8, 3, 0, 1, 0),  # line interleave: a lane gathers its component from RGBRGB... rows
-    "odd8": (4095, 4096, 8, 1, 0, 0, 0),      # rows of 4095 bytes: tightly packed they are not 4-byte aligned (--row-pitch 4096: tiles)
+    "odd8": (4095, 4096, 8, 1, 0, 0, 0),      # rows of 4095 bytes, tightly packed (--row-pitch 4096: no copy needed)
 }
 METRIC = "MPixels/s encode+decode"
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcharls_ref.so")
@@ -773,8 +774,9 @@ def run_gpu_arm(args):
                 "algorithmic_bytes_per_launch": algorithmic}
 
     fast = args.restart_interval == 1
-    # the per-lane kernels without shared-memory tiles: line interleave, and a distance between rows that is not a multiple of 4
-    tiled = ilv != 1 and (args.row_pitch or w * cc * (1 if bits <= 8 else 2)) % 4 == 0
+    # the per-lane kernels without shared-memory tiles: line interleave only (device frames whose rows do not start on word
+    # boundaries are copied to an aligned pitch around the tile kernels, Engine::repitch: in `value`, not in the kernel's time)
+    tiled = ilv != 1
     family = ("tiled" if tiled else "fast") if fast else "general"
     roofs = {"encode": roof(f"k_encode_{family}", t_enc), "decode": roof(f"k_decode_{family}", t_dec)}
     dominant = dict(roofs["encode"] if t_enc >= t_dec else roofs["decode"])

@@ -90,7 +90,8 @@ Engine::~Engine()
         cudaSetDevice(device_);
     for (Buffer* b : {&pixels_, &stream_buffer_, &slots_, &interval_bytes_, &interval_offset_, &line_scratch_, &job_table_,
                       &outcomes_, &marker_counts_, &marker_totals_, &marker_codes_, &header_, &pointer_table_, &prefixes_,
-                      &host_outcomes_, &host_jobs_, &host_prefixes_, &host_pointer_table_})
+                      &repitched_, &row_pointers_, &host_outcomes_, &host_jobs_, &host_prefixes_, &host_pointer_table_,
+                      &host_row_pointers_})
         release(*b);
     for (auto& event : events_)
         if (event)
@@ -809,6 +810,65 @@ int32_t Engine::decode_scan_to_host_end(size_t& consumed)
 // ---------------------------------------------------------------------------------------------------------------------
 // Batch path: device-resident frames
 // ---------------------------------------------------------------------------------------------------------------------
+// Device frames whose rows do not start on 4-byte boundaries (a stride that is not a multiple of four, or such a frame
+// address) would take the kernels without shared-memory tiles, at half the speed or less (profiles/r2_notes.md).  One pass
+// of this kernel copies them to an aligned pitch in front of the encoder, or back behind the decoder: 2 x 2.1 GB for 128 frames
+// of 4095 x 4096, about a millisecond, against 4 (encode) and 11 ms (decode) lost otherwise.
+namespace {
+
+__global__ void k_repitch(uint8_t* const* __restrict__ user_frames, size_t user_stride, uint8_t* __restrict__ scratch, size_t span,
+                          size_t pitch, uint32_t row_bytes, uint32_t height, uint32_t count, bool to_scratch)
+{
+    const uint32_t words = (row_bytes + 3U) / 4U;
+    for (uint32_t f = blockIdx.z; f < count; f += gridDim.z)
+    {
+        uint8_t* const frame = user_frames[f];
+        for (uint32_t row = blockIdx.y; row < height; row += gridDim.y)
+        {
+            for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < words; t += gridDim.x * blockDim.x)
+            {
+                uint8_t* user = frame + static_cast<size_t>(row) * user_stride + 4U * t;
+                uint32_t* aligned = reinterpret_cast<uint32_t*>(scratch + static_cast<size_t>(f) * span + static_cast<size_t>(row) * pitch) + t;
+                const uint32_t n = row_bytes - 4U * t < 4U ? row_bytes - 4U * t : 4U;
+                if (to_scratch)
+                {
+                    uint32_t word = 0;
+                    for (uint32_t b = 0; b < n; ++b)
+                        word |= static_cast<uint32_t>(user[b]) << (8U * b);
+                    *aligned = word;
+                }
+                else
+                {
+                    const uint32_t word = *aligned;
+                    for (uint32_t b = 0; b < n; ++b)
+                        user[b] = static_cast<uint8_t>(word >> (8U * b));
+                }
+            }
+        }
+    }
+}
+
+} // namespace
+
+int32_t Engine::repitch(const BatchFrame* frames, size_t count, size_t stride, size_t pitch, size_t span, uint32_t row_bytes,
+                        uint32_t height, bool to_scratch, CUstream_st* stream)
+{
+    JLS_CHECK(ensure(row_pointers_, count * sizeof(void*)));
+    JLS_CHECK(ensure(host_row_pointers_, count * sizeof(void*), true));
+    auto** host_pointers = static_cast<uint8_t**>(host_row_pointers_.data);
+    for (size_t i = 0; i < count; ++i)
+        host_pointers[i] = frames[i].pixels;
+    JLS_CUDA(cudaMemcpyAsync(row_pointers_.data, host_row_pointers_.data, count * sizeof(void*), cudaMemcpyHostToDevice, stream));
+    const uint32_t words = (row_bytes + 3U) / 4U;
+    const dim3 block(256);
+    const dim3 grid((words + 255U) / 256U, height < 65535U ? height : 65535U, count < 65535U ? static_cast<uint32_t>(count) : 65535U);
+    k_repitch<<<grid, block, 0, stream>>>(static_cast<uint8_t* const*>(row_pointers_.data), stride, static_cast<uint8_t*>(repitched_.data),
+                                          span, pitch, row_bytes, height, static_cast<uint32_t>(count), to_scratch);
+    JLS_CUDA(cudaGetLastError());
+    count_kernel_launches(1);
+    return 0;
+}
+
 int32_t Engine::encode_batch(const CodecParams& p, const uint8_t* header, size_t header_size, BatchFrame* frames, size_t count,
                              size_t stride, CUstream_st* user_stream, const std::function<int32_t()>& while_coding,
                              const StreamOffsetTable* table)
@@ -858,6 +918,19 @@ int32_t Engine::encode_batch_begin(const CodecParams& p, const uint8_t* header, 
             for (uint32_t segment = 0; segment < offset_table_segment_count(table->total); ++segment)
                 job.offset_table.entries[segment] = frames[i].stream + table->entry_offsets[segment];
         }
+    }
+    if (!word_aligned && use_fast_path(p) && p.interleave != ilv_line)
+    {
+        const size_t row_bytes = row_bytes_of(p);
+        const size_t pitch = align_up(row_bytes, 16), span = align_up(pitch * static_cast<size_t>(p.height), 256);
+        JLS_CHECK(ensure(repitched_, count * span + 64));
+        JLS_CHECK(repitch(frames, count, stride, pitch, span, static_cast<uint32_t>(row_bytes), p.height, true, stream));
+        for (size_t i = 0; i < count; ++i)
+        {
+            jobs[i].pixels_in = static_cast<const uint8_t*>(repitched_.data) + i * span;
+            jobs[i].stride = pitch;
+        }
+        word_aligned = pitch < (size_t{1} << 30);
     }
     JLS_CHECK(stage_jobs(p, jobs, true, slot_bytes, stream));
     const ScanJob* device_jobs = static_cast<const ScanJob*>(job_table_.data);
@@ -1246,6 +1319,20 @@ int32_t Engine::decode_batch_begin(const CodecParams& p, const BatchFrame* frame
                 job.offset_table.entries[segment] = frames[i].stream + frames[i].table.entry_offsets[segment];
         }
     }
+    const bool through_scratch = !word_aligned && use_fast_path(p) && p.interleave != ilv_line;
+    const size_t scratch_row_bytes = row_bytes_of(p);
+    const size_t scratch_pitch = align_up(scratch_row_bytes, 16), scratch_span = align_up(scratch_pitch * static_cast<size_t>(p.height), 256);
+    if (through_scratch)
+    {
+        // decoded at an aligned pitch, copied to the caller's rows afterwards (see k_repitch)
+        JLS_CHECK(ensure(repitched_, count * scratch_span + 64));
+        for (size_t i = 0; i < count; ++i)
+        {
+            jobs[i].pixels_out = static_cast<uint8_t*>(repitched_.data) + i * scratch_span;
+            jobs[i].stride = scratch_pitch;
+        }
+        word_aligned = scratch_pitch < (size_t{1} << 30);
+    }
     JLS_CHECK(ensure(marker_counts_, marker_scratch_bytes(count, max_remaining)));
     JLS_CHECK(ensure(marker_totals_, count * sizeof(uint32_t)));
     JLS_CHECK(ensure(marker_codes_, count * p.interval_count));
@@ -1253,6 +1340,9 @@ int32_t Engine::decode_batch_begin(const CodecParams& p, const BatchFrame* frame
     JLS_CUDA(launch_decode(p, static_cast<const ScanJob*>(job_table_.data), static_cast<uint32_t>(count), max_remaining,
                            static_cast<uint32_t*>(marker_counts_.data), static_cast<uint32_t*>(marker_totals_.data),
                            static_cast<uint8_t*>(marker_codes_.data), stream, events_, word_aligned, use_tables));
+    if (through_scratch)
+        JLS_CHECK(repitch(frames, count, stride, scratch_pitch, scratch_span, static_cast<uint32_t>(scratch_row_bytes), p.height, false,
+                          stream));
     JLS_CHECK(ensure(host_outcomes_, count * outcome_words * sizeof(uint64_t), true));
     JLS_CUDA(cudaMemcpyAsync(host_outcomes_.data, outcomes_.data, count * outcome_words * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                              stream));

@@ -171,8 +171,11 @@ private:
     CUstream_st* stream_{};
     int device_{-1};
     Buffer pixels_, stream_buffer_, slots_, interval_bytes_, interval_offset_, line_scratch_, job_table_, outcomes_, table_buffer_,
-        marker_counts_, marker_totals_, marker_codes_, header_, pointer_table_, prefixes_;
-    Buffer host_outcomes_, host_jobs_, host_prefixes_, host_pointer_table_; // pinned
+        marker_counts_, marker_totals_, marker_codes_, header_, pointer_table_, prefixes_, repitched_, row_pointers_;
+    Buffer host_outcomes_, host_jobs_, host_prefixes_, host_pointer_table_, host_row_pointers_; // pinned
+    // device frames whose rows are not 4-byte aligned: copied to / from an aligned pitch around the tile kernels (engine.cu)
+    int32_t repitch(const BatchFrame* frames, size_t count, size_t stride, size_t pitch, size_t span, uint32_t row_bytes,
+                    uint32_t height, bool to_scratch, CUstream_st* stream);
     size_t uploaded_stream_size_{};
     uint32_t last_launches_{};
     float last_coder_ms_{};

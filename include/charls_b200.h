@@ -386,9 +386,10 @@ typedef struct charlsx_batch_params
     charls_interleave_mode interleave_mode; /* none requires component_count == 1 in the batch interface */
     charls_color_transformation color_transformation;
     uint32_t restart_interval; /* encode: interval to write (1 = per line); decode: ignored (read from each stream) */
-    uint32_t stride;           /* bytes between lines of `pixels`, 0 = tightly packed.  Device frames: make it a multiple of 4 --
-                                * other strides (and line interleave) take kernels without shared-memory tiles, at about half
-                                * the speed; host frames are re-pitched on their way to the device. */
+    uint32_t stride;           /* bytes between lines of `pixels`, 0 = tightly packed.  Device frames: a multiple of 4 (and
+                                * 4-byte aligned frames) saves a copy -- other rows are moved to an aligned pitch in device scratch
+                                * memory (one more frame's worth per frame) in front of the encoder and back behind the decoder;
+                                * host frames are re-pitched on their way to the device. */
     uint32_t flags;            /* CHARLSX_BATCH_* */
 } charlsx_batch_params;
 

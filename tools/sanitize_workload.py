@@ -113,7 +113,7 @@ def main():
     from charls_b200.batch import BatchCodec
 
     for table in (False, True):
-        for (w, h, bits, cc, ilv, xf) in ((96, 40, 8, 1, 0, 0), (64, 33, 16, 3, 2, 1)):
+        for (w, h, bits, cc, ilv, xf) in ((96, 40, 8, 1, 0, 0), (64, 33, 16, 3, 2, 1), (131, 40, 8, 1, 0, 0), (33, 35, 16, 3, 2, 1)):
             frames = np.stack([image(h, w, bits, cc, 500 + i, "interleaved", "smooth") for i in range(3)])
             dev = torch.from_numpy(frames.view(np.int16) if bits > 8 else frames).cuda()
             bc = BatchCodec(w, h, bits, cc, interleave_mode=ilv, color_transformation=xf, offset_table=table)
